@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json metric: rendered Mpixels/s forward+backward @ 1M Gaussians, 1080p.
+
+A "step" is one pass of the hot path over one synthetic view: the five per-Gaussian operators
+(with Jacobians, as training calls them), splat, splatB and the Jacobian chain to parameter
+gradients, driven through the `gsplatcu` operator surface by the GSFunction mirror
+(easygaussiansplatting_b200/gsfunction.py == reference gsplat/gsmodel.py:6-93).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+ours, N == 1   config[1] of BASELINE.json: 1M synthetic Gaussians, 1920x1080, SH degree 3.
+ours, N  > 1   multi-view data parallel: the same shared Gaussians, one camera per
+               rank per step, NCCL all-reduce (sum) of the parameter gradients; weak scaling
+               in views, value = total pixels of all ranks / max-over-ranks time.
+reference      the CPU restatement of the reference algorithm (oracle/, OpenMP, all host
+               threads) on a bounded crop of the same workload; rank 0 only.
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "rendered Mpixels/s fwd+bwd @1M Gaussians 1080p; grad max-rel-err vs CPU"
+N_GAUSS, WIDTH, HEIGHT, SH_DIM = 1_000_000, 1920, 1080, 48
+CROP_ROWS = 128  # CPU sample: rows [476, 604) of the frame (8 tile rows, 11.9 % of the pixels)
+CROP_Y0 = 476
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------ CPU arm (oracle port)
+def cpu_sample(steps=1, warmup=0):
+    """forward + backward of the reference algorithm on the host: per-Gaussian stages with
+    Jacobians, tile binning + sort, per-pixel compositing, its backward and the Jacobian chain,
+    on rows [476,604) of the 1080p view of the 1M-Gaussian scene.  Returns (Mpix/s, sec/step,
+    threads, dict of oracle results for the GPU cross-check)."""
+    from oracle import oracle as orc
+    from easygaussiansplatting_b200.scene import synthetic_scene, upstream_gradient
+    sc = synthetic_scene(N_GAUSS, WIDTH, HEIGHT, sh_dim=SH_DIM, seed=0)
+    W, H = WIDTH, CROP_ROWS
+    cy = sc["cy"] - CROP_Y0
+    dl = upstream_gradient(WIDTH, HEIGHT, 0)[:, CROP_Y0:CROP_Y0 + CROP_ROWS, :].copy() * (3.0 * WIDTH * HEIGHT)
+    f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32)
+    times, out = [], None
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        us, pcs, depths, Ju = orc.project(sc["pws"], sc["Rcw"], sc["tcw"], sc["fx"], sc["fy"], sc["cx"], cy)
+        d32 = f32(depths)
+        c3, J3r, J3s = orc.compute_cov3d(sc["rots"], sc["scales"], d32)
+        c2, J2c, J2p = orc.compute_cov2d(f32(c3), f32(pcs), sc["Rcw"], d32, sc["fx"], sc["fy"], W, H)
+        col, Jcs, Jcp = orc.sh2color(sc["shs"], sc["pws"], sc["twc"])
+        ci, areas, Jci = orc.inverse_cov2d(f32(c2), d32)
+        fwd = orc.splat(H, W, f32(us), f32(ci), sc["alphas"], d32, f32(col), areas)
+        g4 = orc.splat_backward(H, W, f32(us), f32(ci), sc["alphas"], f32(col), fwd, dl)
+        grads = orc.chain_backward(sc["Rcw"], *g4, Ju, J3r, J3s, J2c, J2p, Jcs, Jcp, Jci)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+        out = dict(fwd=fwd, grads=grads, scene=sc, cy=cy, dl=dl)
+    sec = statistics.median(times)
+    return W * H / sec / 1e6, sec, orc.num_threads(), out
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    mpix, sec, threads, _ = cpu_sample(steps=max(1, args.steps), warmup=min(1, args.warmup))
+    sample = ("rows %d-%d of the 1920x1080 view (%dx%d px, %.1f%% of the frame), all 1M Gaussians, fwd+bwd"
+              % (CROP_Y0, CROP_Y0 + CROP_ROWS, WIDTH, CROP_ROWS, 100.0 * CROP_ROWS / HEIGHT))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": mpix, "unit": "Mpixels/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "config2: 1M synthetic Gaussians, 1920x1080, SH deg 3, fwd+bwd (CPU: bounded crop)",
+                   "gaussians": N_GAUSS, "width": WIDTH, "height": HEIGHT, "sh_dim": SH_DIM},
+        "cpu_baseline": {"value": mpix, "unit": "Mpixels/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": mpix, "unit": "Mpixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx = float(f[2])
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------ our arm
+def run_ours(args, rank, world):
+    import torch
+    import torch.distributed as dist
+    from easygaussiansplatting_b200 import _lib
+    from easygaussiansplatting_b200.gsfunction import Camera, GSFunction
+    from easygaussiansplatting_b200.scene import ring_camera, synthetic_scene, upstream_gradient
+
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+
+    sc = synthetic_scene(N_GAUSS, WIDTH, HEIGHT, sh_dim=SH_DIM, seed=0)  # shared by all ranks
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    if world > 1:
+        Rcw, tcw, twc = ring_camera(rank, world)
+    else:
+        Rcw, tcw, twc = sc["Rcw"], sc["tcw"], sc["twc"]
+    cam = Camera(WIDTH, HEIGHT, sc["fx"], sc["fy"], sc["cx"], sc["cy"], T(Rcw), T(tcw), T(twc))
+    params = {k: T(sc[k]).requires_grad_() for k in ("pws", "shs", "scales", "rots")}
+    alphas = T(sc["alphas"][:, None]).requires_grad_()
+    us0 = torch.zeros((N_GAUSS, 2), device=dev, requires_grad=True)
+    leaves = [params["pws"], params["shs"], alphas, params["scales"], params["rots"]]
+    dl_host = torch.from_numpy(upstream_gradient(WIDTH, HEIGHT, rank) * (3.0 * WIDTH * HEIGHT)).pin_memory()
+    dl_dev = dl_host.to(dev)
+    cam_host = torch.from_numpy(np.concatenate([Rcw.reshape(-1), tcw, twc]).astype(np.float32)).pin_memory()
+    cam_dev = torch.empty(15, device=dev)
+    img_host = torch.empty((3, HEIGHT, WIDTH), dtype=torch.float32).pin_memory()
+    chk_host = torch.empty(1, dtype=torch.float32).pin_memory()
+
+    def step(dl):
+        for p in leaves:
+            p.grad = None
+        image, _ = GSFunction.apply(params["pws"], params["shs"], alphas, params["scales"], params["rots"], us0, cam)
+        image.backward(dl)
+        if world > 1:  # multi-view DP: sum the parameter gradients over the views
+            flat = torch.cat([p.grad.reshape(-1) for p in leaves])
+            dist.all_reduce(flat)
+        return image
+
+    def step_e2e():
+        # host -> device: this view's camera and dL/dimage; device -> host: image + a gradient checksum
+        cam_dev.copy_(cam_host, non_blocking=True)
+        cam.Rcw, cam.tcw, cam.twc = cam_dev[:9].view(3, 3), cam_dev[9:12], cam_dev[12:15]
+        dl_dev.copy_(dl_host, non_blocking=True)
+        image = step(dl_dev)
+        img_host.copy_(image.detach(), non_blocking=True)
+        chk_host.copy_(params["pws"].grad.abs().sum().reshape(1), non_blocking=True)
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            dist.barrier()
+            tt = torch.tensor([ms], device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms = tt.item()
+        return ms
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = lib.gsb_profile_launches(-1)
+    ms_dev = timed(lambda: step(dl_dev), args.steps, args.warmup)
+    launches = lib.gsb_profile_launches(-1) - launches0
+    launches_timed = launches * args.steps // (args.steps + args.warmup)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_e2e = timed(step_e2e, args.steps, max(1, args.warmup // 2))
+    pix = WIDTH * HEIGHT * world
+    value = pix * args.steps / (ms_dev * 1e-3) / 1e6
+    e2e = pix * args.steps / (ms_e2e * 1e-3) / 1e6
+
+    # ---- per-kernel durations with CUDA events on the launch stream (roofline leg)
+    import ctypes as C
+    prof_steps = 5
+    lib.gsb_profile_enable(1)
+    for _ in range(prof_steps):
+        image = step(dl_dev)
+    torch.cuda.synchronize()
+    lib.gsb_profile_enable(0)
+    kern = {}
+    for i in range(lib.gsb_profile_kernels()):
+        ms_tot, cnt = C.c_double(0), C.c_longlong(0)
+        lib.gsb_profile_read(i, C.byref(ms_tot), C.byref(cnt))
+        if cnt.value:
+            kern[lib.gsb_profile_kernel_name(i).decode()] = ms_tot.value / prof_steps
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- algorithmic bytes of the dominant kernel (SURVEY 8d / BASELINE.md 3)
+    with torch.no_grad():
+        import gsplatcu as gsc
+        us, pcs, depths = gsc.project(params["pws"], cam.Rcw, cam.tcw, cam.fx, cam.fy, cam.cx, cam.cy, False)
+        c3 = gsc.computeCov3D(params["rots"], params["scales"], depths, False)[0]
+        c2 = gsc.computeCov2D(c3, pcs, cam.Rcw, depths, cam.fx, cam.fy, WIDTH, HEIGHT, False)[0]
+        col = gsc.sh2Color(params["shs"], params["pws"], cam.twc, False)[0]
+        ci, areas = gsc.inverseCov2D(c2, depths, False)
+        img, contrib, ftau, ranges, gsid = gsc.splat(HEIGHT, WIDTH, us, ci, alphas, depths, col, areas)
+        P = gsid.numel()
+        gy, gx = (HEIGHT + 15) // 16, (WIDTH + 15) // 16
+        pad = torch.zeros((gy * 16, gx * 16), dtype=torch.int32, device=dev)
+        pad[:HEIGHT, :WIDTH] = contrib
+        p_eff = int(pad.view(gy, 16, gx, 16).amax(dim=(1, 3)).sum().item())
+    Tn = gx * gy
+    WH = WIDTH * HEIGHT
+    alg = {"draw_backward": 44 * p_eff + 8 * Tn + 20 * WH + 36 * N_GAUSS,
+           "draw": 44 * p_eff + 8 * Tn + 20 * WH}
+    top = max(kern, key=kern.get)
+    roof_k = top if top in alg else "draw_backward"
+    peak, peak_src = peaks()
+    achieved = alg[roof_k] / (kern[roof_k] * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": roof_k, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg[roof_k], "kernel_ms": kern[roof_k],
+                "note": "draw/draw_backward are FP32/MUFU-issue bound on dense scenes (SURVEY 8d); "
+                        "see profiles/ for pipe utilisation"}
+
+    # ---- CPU baseline + gradient error vs CPU on the same crop
+    cpu_mpix, cpu_sec, cpu_threads, cpu = cpu_sample(steps=1, warmup=0)
+    grad_err = gpu_vs_cpu_crop(torch, dev, cpu)
+    line = {
+        "metric": METRIC, "value": value, "unit": "Mpixels/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "config2: 1M synthetic Gaussians, 1920x1080, SH deg 3, fwd+bwd through the "
+                               "gsplatcu operator surface (calc_J=True) + Jacobian chain",
+                   "gaussians": N_GAUSS, "width": WIDTH, "height": HEIGHT, "sh_dim": SH_DIM, "patches": P,
+                   "p_eff": p_eff, "views_per_step": world,
+                   "parallelism": "1 view/rank, shared Gaussians, NCCL all-reduce of param grads" if world > 1 else "single GPU",
+                   "l2": "per-step working set ~1.5 GB (Jacobians + SH + records) >> 126 MB L2; no explicit flush"},
+        "gaussians_per_s": N_GAUSS * world * args.steps / (ms_dev * 1e-3),
+        "grad_max_rel_err_vs_cpu": grad_err,
+        "roofline": roofline,
+        "kernel_ms_per_step": kern,
+        "cpu_baseline": {"value": cpu_mpix, "unit": "Mpixels/s", "cores": cpu_threads, "kind": "port",
+                         "sample": "rows %d-%d of the 1080p view (%dx%d px), all 1M Gaussians, fwd+bwd, %.1f s"
+                                   % (CROP_Y0, CROP_Y0 + CROP_ROWS, WIDTH, CROP_ROWS, cpu_sec)},
+        "e2e": {"value": e2e, "unit": "Mpixels/s", "ms_per_step": ms_e2e / args.steps,
+                "h2d_bytes_per_step": int(dl_host.numel() * 4 + cam_host.numel() * 4),
+                "d2h_bytes_per_step": int(img_host.numel() * 4 + 4)},
+        "gpu_launches": int(launches_timed),
+        "clocks": clocks,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def gpu_vs_cpu_crop(torch, dev, cpu):
+    """max over parameter tensors of max|g_gpu - g_cpu| / max|g_cpu| on the CPU sample crop"""
+    from easygaussiansplatting_b200.gsfunction import Camera, GSFunction
+    sc, cy, dl = cpu["scene"], cpu["cy"], cpu["dl"]
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    cam = Camera(WIDTH, CROP_ROWS, sc["fx"], sc["fy"], sc["cx"], cy, T(sc["Rcw"]), T(sc["tcw"]), T(sc["twc"]))
+    P = {k: T(sc[k]).requires_grad_() for k in ("pws", "shs", "scales", "rots")}
+    al = T(sc["alphas"][:, None]).requires_grad_()
+    us0 = torch.zeros((N_GAUSS, 2), device=dev, requires_grad=True)
+    image, _ = GSFunction.apply(P["pws"], P["shs"], al, P["scales"], P["rots"], us0, cam)
+    image.backward(T(dl))
+    worst = 0.0
+    for name, got in (("pws", P["pws"].grad), ("shs", P["shs"].grad), ("scales", P["scales"].grad),
+                      ("rots", P["rots"].grad), ("alphas", al.grad)):
+        ref = cpu["grads"][name]
+        e = np.abs(got.cpu().numpy().reshape(ref.shape) - ref).max() / max(np.abs(ref).max(), 1e-30)
+        worst = max(worst, float(e))
+    return worst
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if args.impl == "reference":
+        run_reference(args, rank)
+    else:
+        run_ours(args, rank, world)
+
+
+if __name__ == "__main__":
+    main()

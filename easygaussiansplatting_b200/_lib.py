@@ -1,0 +1,58 @@
+"""ctypes loader for libgsplat_b200.so (include/gsplat_b200.h).  There is NO fallback:
+if the library is missing or an entry point fails, the operators raise."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgsplat_b200.so")
+
+_vp, _i, _f, _i64, _sz = C.c_void_p, C.c_int, C.c_float, C.c_int64, C.c_size_t
+
+# name -> (restype, argtypes); mirrors include/gsplat_b200.h one to one
+SIGNATURES = {
+    "gsb_abi_version": (_i, []),
+    "gsb_last_error": (C.c_char_p, []),
+    "gsb_project": (_i, [_i, _vp, _vp, _vp, _f, _f, _f, _f, _vp, _vp, _vp, _vp, _vp]),
+    "gsb_compute_cov3d": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "gsb_compute_cov2d": (_i, [_i, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _vp, _vp, _vp, _vp]),
+    "gsb_sh2color": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "gsb_inverse_cov2d": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "gsb_splat_bin_workspace_bytes": (_sz, [_i]),
+    "gsb_splat_bin": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _sz, C.POINTER(_i64), _vp]),
+    "gsb_splat_workspace_bytes": (_sz, [_i, _i, _i, _i64]),
+    "gsb_splat_render": (_i, [_i, _i, _i, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _vp,
+                              _vp, _vp, _vp, _vp]),
+    "gsb_splat_backward_workspace_bytes": (_sz, [_i, _i, _i, _i64]),
+    "gsb_splat_backward": (_i, [_i, _i, _i, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                _sz, _vp, _vp, _vp, _vp, _vp]),
+    "gsb_profile_enable": (None, [_i]),
+    "gsb_profile_kernels": (_i, []),
+    "gsb_profile_kernel_name": (C.c_char_p, [_i]),
+    "gsb_profile_launches": (C.c_longlong, [_i]),
+    "gsb_profile_read": (_i, [_i, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
+}
+
+_lib = None
+
+
+def load():
+    """Returns the CDLL with every entry point typed; raises if the library is not built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                "libgsplat_b200.so is not built (%s). Run `python -m easygaussiansplatting_b200.build` "
+                "or __graft_entry__.build(); there is no CPU / PyTorch fallback." % LIB_PATH)
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)  # AttributeError if the ABI drifted
+            fn.restype, fn.argtypes = res, args
+        if lib.gsb_abi_version() != 1:
+            raise ImportError("libgsplat_b200.so ABI version mismatch")
+        _lib = lib
+    return _lib
+
+
+def check(rc, lib):
+    if rc != 0:
+        raise RuntimeError("gsplat_b200: %s (rc=%d)" % (lib.gsb_last_error().decode(), rc))

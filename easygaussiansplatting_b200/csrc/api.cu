@@ -1,0 +1,228 @@
+// extern "C" entry points declared in include/gsplat_b200.h.
+#include <stdio.h>
+#include <string.h>
+
+#include <mutex>
+#include <vector>
+
+#include "../../include/gsplat_b200.h"
+#include "common.cuh"
+#include "kernels.h"
+
+namespace gsb {
+
+static thread_local char g_err[512] = "";
+
+int set_cuda_error(cudaError_t e, const char *what, const char *file, int line) {
+  snprintf(g_err, sizeof(g_err), "CUDA error %d (%s) in %s at %s:%d", (int)e, cudaGetErrorString(e), what,
+           file, line);
+  return (int)e;
+}
+int set_arg_error(const char *msg) {
+  snprintf(g_err, sizeof(g_err), "argument error: %s", msg);
+  return -1;
+}
+
+// ---- profiling
+static bool g_prof_on = false;
+static long long g_launches[K_COUNT] = {0};
+struct EvPair { cudaEvent_t a, b; };
+static std::vector<EvPair> g_events[K_COUNT];
+static std::mutex g_prof_mu;
+static const char *const g_names[K_COUNT] = {"project", "computeCov3D", "computeCov2D", "sh2Color",
+                                             "inverseCov2D", "rects", "scan(cub)", "keys", "sort(cub)",
+                                             "ranges", "pack_records", "draw", "draw_backward"};
+
+ProfScope::ProfScope(int id, cudaStream_t st) : id_(id), st_(st), stop_(nullptr) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_launches[id]++;
+  if (g_prof_on) {
+    EvPair e;
+    if (cudaEventCreate(&e.a) == cudaSuccess && cudaEventCreate(&e.b) == cudaSuccess) {
+      cudaEventRecord(e.a, st);
+      stop_ = e.b;
+      g_events[id].push_back(e);
+    }
+  }
+}
+ProfScope::~ProfScope() {
+  if (stop_) cudaEventRecord(stop_, st_);
+}
+
+}  // namespace gsb
+
+using namespace gsb;
+
+#define GSB_REQUIRE(cond, msg) \
+  do {                         \
+    if (!(cond)) return set_arg_error(msg); \
+  } while (0)
+
+extern "C" {
+
+int gsb_abi_version(void) { return GSB_ABI_VERSION; }
+const char *gsb_last_error(void) { return g_err; }
+
+int gsb_project(int N, const float *pws, const float *Rcw, const float *tcw, float fx, float fy,
+                float cx, float cy, float *us, float *pcs, float *depths, float *du_dpcs,
+                gsb_stream_t stream) {
+  GSB_REQUIRE(N >= 0, "project: N < 0");
+  GSB_REQUIRE(N == 0 || (pws && Rcw && tcw && us && pcs && depths), "project: null pointer");
+  return launch_project(N, pws, Rcw, tcw, fx, fy, cx, cy, us, pcs, depths, du_dpcs, (cudaStream_t)stream);
+}
+
+int gsb_compute_cov3d(int N, const float *rots, const float *scales, const float *depths,
+                      float *cov3ds, float *dcov3d_drots, float *dcov3d_dscales, gsb_stream_t stream) {
+  GSB_REQUIRE(N >= 0, "computeCov3D: N < 0");
+  GSB_REQUIRE(N == 0 || (rots && scales && depths && cov3ds), "computeCov3D: null pointer");
+  GSB_REQUIRE((dcov3d_drots == nullptr) == (dcov3d_dscales == nullptr),
+              "computeCov3D: Jacobian outputs must be both set or both null");
+  return launch_cov3d(N, rots, scales, depths, cov3ds, dcov3d_drots, dcov3d_dscales, (cudaStream_t)stream);
+}
+
+int gsb_compute_cov2d(int N, const float *cov3ds, const float *pcs, const float *Rcw,
+                      const float *depths, float fx, float fy, float width, float height,
+                      float *cov2ds, float *dcov2d_dcov3ds, float *dcov2d_dpcs, gsb_stream_t stream) {
+  GSB_REQUIRE(N >= 0, "computeCov2D: N < 0");
+  GSB_REQUIRE(N == 0 || (cov3ds && pcs && Rcw && depths && cov2ds), "computeCov2D: null pointer");
+  GSB_REQUIRE((dcov2d_dcov3ds == nullptr) == (dcov2d_dpcs == nullptr),
+              "computeCov2D: Jacobian outputs must be both set or both null");
+  return launch_cov2d(N, cov3ds, pcs, Rcw, depths, fx, fy, width, height, cov2ds, dcov2d_dcov3ds,
+                      dcov2d_dpcs, (cudaStream_t)stream);
+}
+
+int gsb_sh2color(int N, int sh_dim3, const float *shs, const float *pws, const float *twc,
+                 float *colors, float *dcolor_dshs, float *dcolor_dpws, gsb_stream_t stream) {
+  GSB_REQUIRE(N >= 0, "sh2Color: N < 0");
+  GSB_REQUIRE(sh_dim3 == 1 || sh_dim3 == 4 || sh_dim3 == 9 || sh_dim3 == 16,
+              "sh2Color: shs.shape[1]/3 must be 1, 4, 9 or 16");
+  GSB_REQUIRE(N == 0 || (shs && pws && twc && colors), "sh2Color: null pointer");
+  GSB_REQUIRE((dcolor_dshs == nullptr) == (dcolor_dpws == nullptr),
+              "sh2Color: Jacobian outputs must be both set or both null");
+  return launch_sh2color(N, sh_dim3, shs, pws, twc, colors, dcolor_dshs, dcolor_dpws, (cudaStream_t)stream);
+}
+
+int gsb_inverse_cov2d(int N, const float *cov2ds, float *depths, float *cinv2ds, int32_t *areas,
+                      float *dcinv2d_dcov2ds, gsb_stream_t stream) {
+  GSB_REQUIRE(N >= 0, "inverseCov2D: N < 0");
+  GSB_REQUIRE(N == 0 || (cov2ds && depths && cinv2ds && areas), "inverseCov2D: null pointer");
+  return launch_inv_cov2d(N, cov2ds, depths, cinv2ds, areas, dcinv2d_dcov2ds, (cudaStream_t)stream);
+}
+
+void gsb_profile_enable(int on) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof_on = on != 0;
+}
+int gsb_profile_kernels(void) { return (int)K_COUNT; }
+const char *gsb_profile_kernel_name(int id) { return (id >= 0 && id < K_COUNT) ? g_names[id] : ""; }
+long long gsb_profile_launches(int id) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (id >= 0 && id < K_COUNT) return g_launches[id];
+  long long t = 0;
+  for (int i = 0; i < K_COUNT; i++) t += g_launches[i];
+  return t;
+}
+int gsb_profile_read(int id, double *ms_total, long long *timed_launches) {
+  GSB_REQUIRE(id >= 0 && id < K_COUNT && ms_total && timed_launches, "profile_read: bad arguments");
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  double tot = 0.0;
+  long long cnt = 0;
+  for (auto &e : g_events[id]) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(e.b) == cudaSuccess && cudaEventElapsedTime(&ms, e.a, e.b) == cudaSuccess) {
+      tot += ms;
+      cnt++;
+    }
+    cudaEventDestroy(e.a);
+    cudaEventDestroy(e.b);
+  }
+  g_events[id].clear();
+  *ms_total = tot;
+  *timed_launches = cnt;
+  return 0;
+}
+
+size_t gsb_splat_bin_workspace_bytes(int N) { return bin_layout(N).bytes; }
+
+int gsb_splat_bin(int H, int W, int N, const float *us, float *depths, int32_t *areas, void *bin_ws,
+                  size_t bin_ws_bytes, int64_t *P_host, gsb_stream_t stream) {
+  GSB_REQUIRE(N >= 0 && H > 0 && W > 0, "splat: bad N/H/W");
+  GSB_REQUIRE(P_host != nullptr && bin_ws != nullptr, "splat: null workspace / P_host");
+  GSB_REQUIRE(N == 0 || (us && depths && areas), "splat: null pointer");
+  const BinLayout L = bin_layout(N);
+  GSB_REQUIRE(bin_ws_bytes >= L.bytes, "splat: bin workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = launch_bin(H, W, N, us, depths, areas, bin_ws, L, st);
+  if (rc) return rc;
+  uint32_t total = 0;
+  GSB_CUDA_TRY(cudaMemcpyAsync(&total, static_cast<char *>(bin_ws) + L.total, sizeof(uint32_t),
+                               cudaMemcpyDeviceToHost, st));
+  GSB_CUDA_TRY(cudaStreamSynchronize(st));
+  *P_host = (int64_t)total;
+  return 0;
+}
+
+size_t gsb_splat_workspace_bytes(int N, int H, int W, int64_t P) {
+  SortLayout L;
+  if (sort_layout(N, H, W, P, &L)) return 0;
+  return L.bytes;
+}
+
+int gsb_splat_render(int H, int W, int N, int64_t P, const float *us, const float *cinv2ds,
+                     const float *alphas, const float *depths, const float *colors, const void *bin_ws,
+                     void *ws, size_t ws_bytes, float *image, int32_t *contrib, float *final_tau,
+                     int32_t *patch_range_per_tile, int32_t *gsid_per_patch, gsb_stream_t stream) {
+  GSB_REQUIRE(N >= 0 && H > 0 && W > 0 && P >= 0, "splat: bad N/H/W/P");
+  GSB_REQUIRE(image && contrib && final_tau && patch_range_per_tile, "splat: null output");
+  GSB_REQUIRE(P == 0 || (us && cinv2ds && alphas && depths && colors && bin_ws && ws && gsid_per_patch),
+              "splat: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  SortLayout SL{};
+  if (P > 0) {
+    int rc = sort_layout(N, H, W, P, &SL);
+    if (rc) return rc;
+    GSB_REQUIRE(ws_bytes >= SL.bytes, "splat: workspace too small");
+  }
+  const BinLayout BL = bin_layout(N);
+  int rc = launch_sort_and_pack(H, W, N, P, us, cinv2ds, alphas, depths, colors, bin_ws, BL, ws, SL,
+                                patch_range_per_tile, gsid_per_patch, st);
+  if (rc) return rc;
+  const Rec *recs = P > 0 ? reinterpret_cast<const Rec *>(static_cast<char *>(ws) + SL.recs) : nullptr;
+  return launch_draw(H, W, patch_range_per_tile, recs, image, contrib, final_tau, st);
+}
+
+size_t gsb_splat_backward_workspace_bytes(int N, int H, int W, int64_t P) {
+  (void)N; (void)H; (void)W;
+  return (size_t)(P > 0 ? P : 1) * sizeof(Rec) + 256;
+}
+
+int gsb_splat_backward(int H, int W, int N, int64_t P, const float *us, const float *cinv2ds,
+                       const float *alphas, const float *colors, const int32_t *contrib,
+                       const float *final_tau, const int32_t *patch_range_per_tile,
+                       const int32_t *gsid_per_patch, const float *dloss_dgammas, void *ws,
+                       size_t ws_bytes, float *dloss_dus, float *dloss_dcinv2ds, float *dloss_dalphas,
+                       float *dloss_dcolors, gsb_stream_t stream) {
+  GSB_REQUIRE(N >= 0 && H > 0 && W > 0 && P >= 0, "splatB: bad N/H/W/P");
+  GSB_REQUIRE(N == 0 || (dloss_dus && dloss_dcinv2ds && dloss_dalphas && dloss_dcolors), "splatB: null output");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (N > 0) {
+    GSB_CUDA_TRY(cudaMemsetAsync(dloss_dus, 0, sizeof(float) * 2 * (size_t)N, st));
+    GSB_CUDA_TRY(cudaMemsetAsync(dloss_dcinv2ds, 0, sizeof(float) * 3 * (size_t)N, st));
+    GSB_CUDA_TRY(cudaMemsetAsync(dloss_dalphas, 0, sizeof(float) * (size_t)N, st));
+    GSB_CUDA_TRY(cudaMemsetAsync(dloss_dcolors, 0, sizeof(float) * 3 * (size_t)N, st));
+  }
+  if (P == 0 || N == 0) return 0;
+  GSB_REQUIRE(us && cinv2ds && alphas && colors && contrib && final_tau && patch_range_per_tile &&
+                  gsid_per_patch && dloss_dgammas && ws,
+              "splatB: null pointer");
+  GSB_REQUIRE(ws_bytes >= gsb_splat_backward_workspace_bytes(N, H, W, P), "splatB: workspace too small");
+  // 256-B align the record stream inside the workspace (cp.async.bulk needs 16 B)
+  uintptr_t base = (reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255;
+  Rec *recs = reinterpret_cast<Rec *>(base);
+  int rc = launch_pack_only(P, gsid_per_patch, us, cinv2ds, alphas, colors, recs, st);
+  if (rc) return rc;
+  return launch_draw_backward(H, W, patch_range_per_tile, recs, contrib, final_tau, dloss_dgammas, dloss_dus,
+                              dloss_dcinv2ds, dloss_dalphas, dloss_dcolors, st);
+}
+
+}  // extern "C"

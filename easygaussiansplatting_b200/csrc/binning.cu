@@ -1,0 +1,243 @@
+// Tile binning: per-Gaussian tile rectangles, exclusive offsets, (tile | depth-mm) keys,
+// duplicate-key radix sort, per-tile ranges and the packed per-patch record stream.
+//
+// Replaces getRects / thrust::inclusive_scan / createKeys / thrust::sort_by_key / getRanges
+// (reference kernel.cu:46-150, gausplat.cu:50-91).  Scan and sort use CUB from the CUDA
+// toolkit (the reference uses the same toolkit's Thrust); everything is stream-ordered in
+// caller-provided workspace (the reference cudaMallocs five device_vectors per call).
+// The sort only covers the bits that can differ: 32 depth bits + ceil(log2(tiles)).
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace gsb {
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// rect packed as (x0 | x1 << 16, y0 | y1 << 16); tile grids up to 65535 x 65535
+__global__ void __launch_bounds__(256) k_rects(int N, const float2 *__restrict__ us,
+                                               int2 *__restrict__ areas, float *__restrict__ depths,
+                                               int gx, int gy, uint2 *__restrict__ rects,
+                                               uint32_t *__restrict__ counts) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  uint32_t n = 0;
+  uint2 rect = make_uint2(0u, 0u);
+  if (!(depths[i] < MIN_DEPTH)) {
+    const float2 u = __ldg(us + i);
+    const int2 ar = areas[i];
+    const float xs = (float)ar.x, ys = (float)ar.y;
+    // kernel.cu:105-110; DIV_ROUND_UP(X,16) on floats is ((X) + 16 - 1) / 16 (common.cuh:15).
+    // Explicit _rn intrinsics: these decide the patch list, no contraction / reassociation.
+    const int x0 = min(gx, max(0, (int)__fdiv_rn(__fsub_rn(u.x, xs), 16.0f)));
+    const int y0 = min(gy, max(0, (int)__fdiv_rn(__fsub_rn(u.y, ys), 16.0f)));
+    const int x1 = min(gx, max(0, (int)__fdiv_rn(__fsub_rn(__fadd_rn(__fadd_rn(u.x, xs), 16.0f), 1.0f), 16.0f)));
+    const int y1 = min(gy, max(0, (int)__fdiv_rn(__fsub_rn(__fadd_rn(__fadd_rn(u.y, ys), 16.0f), 1.0f), 16.0f)));
+    n = (uint32_t)(y1 - y0) * (uint32_t)(x1 - x0);
+    if (n == 0) {  // kernel.cu:114-119: in-place cull
+      depths[i] = BAD_MARKER;
+      areas[i] = make_int2(0, 0);
+    } else {
+      rect = make_uint2((uint32_t)x0 | ((uint32_t)x1 << 16), (uint32_t)y0 | ((uint32_t)y1 << 16));
+    }
+  }
+  rects[i] = rect;
+  counts[i] = n;
+}
+
+__global__ void k_total(int N, const uint32_t *__restrict__ incl, uint32_t *__restrict__ total) {
+  *total = N > 0 ? incl[N - 1] : 0u;
+}
+
+// one thread per Gaussian, serial over its rectangle (2.5 patches/Gaussian on the
+// benchmark scenes).  key = tile << 32 | (uint32)(depth * 1000)   (kernel.cu:71-74)
+__global__ void __launch_bounds__(256) k_keys(int N, const float *__restrict__ depths,
+                                              const uint32_t *__restrict__ incl,
+                                              const uint2 *__restrict__ rects, int gx,
+                                              uint64_t *__restrict__ keys, int32_t *__restrict__ vals) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const float d = __ldg(depths + i);
+  if (d < MIN_DEPTH) return;
+  uint32_t off = (i == 0) ? 0u : __ldg(incl + i - 1);
+  const uint2 r = __ldg(rects + i);
+  const uint32_t x0 = r.x & 0xffffu, x1 = r.x >> 16, y0 = r.y & 0xffffu, y1 = r.y >> 16;
+  const uint32_t dk = __float2uint_rz(__fmul_rn(d, 1000.0f));
+  for (uint32_t y = y0; y < y1; y++)
+    for (uint32_t x = x0; x < x1; x++) {
+      keys[off] = ((uint64_t)(y * (uint32_t)gx + x) << 32) | dk;
+      vals[off] = i;
+      off++;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_ranges(int64_t P, const uint64_t *__restrict__ keys,
+                                                int2 *__restrict__ ranges) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  const uint32_t t = (uint32_t)(keys[p] >> 32);
+  if (p == 0 || (uint32_t)(keys[p - 1] >> 32) != t) ranges[t].x = (int)p;
+  if (p == P - 1 || (uint32_t)(keys[p + 1] >> 32) != t) ranges[t].y = (int)(p + 1);
+}
+
+// Gathers the four per-Gaussian attribute arrays (all L2 resident: 36 B/Gaussian) into the
+// sorted 48-B record stream the rasterizer streams with cp.async.bulk.
+// hx, hy: conservative half-extents of the region where alpha' can reach 0.002, i.e.
+// maha <= 2 ln(alpha / 0.002); computed in fp64 so the determinant does not cancel.
+__global__ void __launch_bounds__(256) k_pack(int64_t P, const int32_t *__restrict__ gsid,
+                                              const float2 *__restrict__ us,
+                                              const float *__restrict__ cinv2ds,
+                                              const float *__restrict__ alphas,
+                                              const float *__restrict__ colors, Rec *__restrict__ recs) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  const int g = __ldg(gsid + p);
+  const float2 u = __ldg(us + g);
+  const float A = __ldg(cinv2ds + 3 * (size_t)g), B = __ldg(cinv2ds + 3 * (size_t)g + 1),
+              C = __ldg(cinv2ds + 3 * (size_t)g + 2);
+  const float al = __ldg(alphas + g);
+  float hx = INFINITY, hy = INFINITY;
+  if (al < ALPHA_SKIP) {
+    hx = hy = -INFINITY;  // alpha * g < 0.002 everywhere: never contributes
+  } else {
+    const double det = (double)A * (double)C - (double)B * (double)B;
+    const double L = 2.0 * log((double)al / 0.002);
+    if (det > 0.0 && A > 0.f && C > 0.f && isfinite(det) && isfinite(L)) {
+      const double ex = sqrt(L * (double)C / det) * 1.00001 + 1e-3;
+      const double ey = sqrt(L * (double)A / det) * 1.00001 + 1e-3;
+      if (isfinite(ex) && isfinite(ey)) {
+        hx = __double2float_ru(ex);
+        hy = __double2float_ru(ey);
+      }
+    }
+  }
+  Rec r;
+  r.q0 = make_float4(u.x, u.y, hx, hy);
+  r.q1 = make_float4(-0.5f * LOG2E * A, -LOG2E * B, -0.5f * LOG2E * C, al);
+  r.q2 = make_float4(__ldg(colors + 3 * (size_t)g), __ldg(colors + 3 * (size_t)g + 1),
+                     __ldg(colors + 3 * (size_t)g + 2), __int_as_float(g));
+  recs[p] = r;
+}
+
+// ---------------------------------------------------------------- phase 1
+BinLayout bin_layout(int N) {
+  BinLayout L{};
+  const size_t n = (size_t)(N > 0 ? N : 1);
+  size_t o = 0;
+  L.rects = o;   o = align_up(o + n * sizeof(uint2), 256);
+  L.counts = o;  o = align_up(o + n * sizeof(uint32_t), 256);
+  L.offsets = o; o = align_up(o + n * sizeof(uint32_t), 256);
+  L.total = o;   o = align_up(o + sizeof(uint32_t), 256);
+  size_t tmp = 0;
+  cub::DeviceScan::InclusiveSum(nullptr, tmp, (uint32_t *)nullptr, (uint32_t *)nullptr, (int)n);
+  L.scan_tmp = o;
+  L.scan_tmp_bytes = tmp > 0 ? tmp : 256;
+  o = align_up(o + L.scan_tmp_bytes, 256);
+  L.bytes = o;
+  return L;
+}
+
+int launch_bin(int H, int W, int N, const float *us, float *depths, int32_t *areas, void *ws,
+               const BinLayout &L, cudaStream_t st) {
+  char *b = static_cast<char *>(ws);
+  uint32_t *total = reinterpret_cast<uint32_t *>(b + L.total);
+  if (N <= 0) {
+    GSB_CUDA_TRY(cudaMemsetAsync(total, 0, sizeof(uint32_t), st));
+    return 0;
+  }
+  const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
+  uint2 *rects = reinterpret_cast<uint2 *>(b + L.rects);
+  uint32_t *counts = reinterpret_cast<uint32_t *>(b + L.counts);
+  uint32_t *incl = reinterpret_cast<uint32_t *>(b + L.offsets);
+  {
+    ProfScope ps(K_RECTS, st);
+    k_rects<<<(N + 255) / 256, 256, 0, st>>>(N, reinterpret_cast<const float2 *>(us),
+                                             reinterpret_cast<int2 *>(areas), depths, gx, gy, rects, counts);
+  }
+  GSB_CUDA_TRY(cudaGetLastError());
+  size_t tmp = L.scan_tmp_bytes;
+  {
+    ProfScope ps(K_SCAN, st);
+    GSB_CUDA_TRY(cub::DeviceScan::InclusiveSum(b + L.scan_tmp, tmp, counts, incl, N, st));
+    k_total<<<1, 1, 0, st>>>(N, incl, total);
+  }
+  GSB_CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------- phase 2
+static int sort_end_bit(int H, int W) {
+  const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
+  const uint64_t T = (uint64_t)gx * (uint64_t)gy;
+  int bits = 0;
+  while (((uint64_t)1 << bits) < T) bits++;
+  return 32 + bits;
+}
+
+int sort_layout(int N, int H, int W, int64_t P, SortLayout *out) {
+  (void)N;
+  SortLayout L{};
+  const size_t n = (size_t)(P > 0 ? P : 1);
+  size_t o = 0;
+  L.keys_a = o; o = align_up(o + n * sizeof(uint64_t), 256);
+  L.keys_b = o; o = align_up(o + n * sizeof(uint64_t), 256);
+  L.vals_a = o; o = align_up(o + n * sizeof(int32_t), 256);
+  L.recs = o;   o = align_up(o + n * sizeof(Rec), 256);
+  size_t tmp = 0;
+  cudaError_t e = cub::DeviceRadixSort::SortPairs(nullptr, tmp, (uint64_t *)nullptr, (uint64_t *)nullptr,
+                                                  (int32_t *)nullptr, (int32_t *)nullptr, (int64_t)n, 0,
+                                                  sort_end_bit(H, W));
+  if (e != cudaSuccess) return set_cuda_error(e, "cub::DeviceRadixSort size query", __FILE__, __LINE__);
+  L.sort_tmp = o;
+  L.sort_tmp_bytes = tmp > 0 ? tmp : 256;
+  o = align_up(o + L.sort_tmp_bytes, 256);
+  L.bytes = o;
+  *out = L;
+  return 0;
+}
+
+int launch_pack_only(int64_t P, const int32_t *gsid_per_patch, const float *us, const float *cinv2ds,
+                     const float *alphas, const float *colors, Rec *recs, cudaStream_t st) {
+  if (P <= 0) return 0;
+  ProfScope ps(K_PACK, st);
+  k_pack<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(P, gsid_per_patch, reinterpret_cast<const float2 *>(us),
+                                                      cinv2ds, alphas, colors, recs);
+  GSB_CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int launch_sort_and_pack(int H, int W, int N, int64_t P, const float *us, const float *cinv2ds,
+                         const float *alphas, const float *depths, const float *colors,
+                         const void *bin_ws, const BinLayout &BL, void *ws, const SortLayout &SL,
+                         int32_t *ranges, int32_t *gsid_per_patch, cudaStream_t st) {
+  const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
+  GSB_CUDA_TRY(cudaMemsetAsync(ranges, 0, sizeof(int32_t) * 2 * (size_t)gx * gy, st));
+  if (P <= 0 || N <= 0) return 0;
+  const char *bb = static_cast<const char *>(bin_ws);
+  char *b = static_cast<char *>(ws);
+  uint64_t *keys_a = reinterpret_cast<uint64_t *>(b + SL.keys_a);
+  uint64_t *keys_b = reinterpret_cast<uint64_t *>(b + SL.keys_b);
+  int32_t *vals_a = reinterpret_cast<int32_t *>(b + SL.vals_a);
+  {
+    ProfScope ps(K_KEYS, st);
+    k_keys<<<(N + 255) / 256, 256, 0, st>>>(N, depths, reinterpret_cast<const uint32_t *>(bb + BL.offsets),
+                                            reinterpret_cast<const uint2 *>(bb + BL.rects), gx, keys_a, vals_a);
+  }
+  GSB_CUDA_TRY(cudaGetLastError());
+  size_t tmp = SL.sort_tmp_bytes;
+  {
+    ProfScope ps(K_SORT, st);
+    GSB_CUDA_TRY(cub::DeviceRadixSort::SortPairs(b + SL.sort_tmp, tmp, keys_a, keys_b, vals_a, gsid_per_patch,
+                                                 P, 0, sort_end_bit(H, W), st));
+  }
+  {
+    ProfScope ps(K_RANGES, st);
+    k_ranges<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(P, keys_b, reinterpret_cast<int2 *>(ranges));
+  }
+  GSB_CUDA_TRY(cudaGetLastError());
+  return launch_pack_only(P, gsid_per_patch, us, cinv2ds, alphas, colors, reinterpret_cast<Rec *>(b + SL.recs), st);
+}
+
+}  // namespace gsb

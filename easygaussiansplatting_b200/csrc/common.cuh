@@ -1,0 +1,102 @@
+// Shared device helpers for the sm_100a kernels: constants fixed by the reference,
+// mbarrier / bulk-async-copy (TMA 1-D, SASS UBLKCP) PTX wrappers, fast math.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace gsb {
+
+constexpr int TILE = 16;              // reference common.cuh:13
+constexpr float MIN_DEPTH = 0.2f;     // kernel.cu:10: (float)z < 0.2 (double)  <=>  z < 0.2f
+constexpr float BAD_MARKER = -1.0f;   // kernel.cu:11
+constexpr float ALPHA_CLAMP = 0.99f;  // kernel.cu:245
+constexpr float ALPHA_SKIP = 0.002f;  // kernel.cu:246
+constexpr float TAU_STOP = 0.0001f;   // kernel.cu:256
+constexpr float LOG2E = 1.4426950408889634f;
+
+// Packed per-patch record, 48 B, written by pack_records (binning.cu) in sorted order so a
+// tile's records are one contiguous 16-B aligned span -> one cp.async.bulk per batch.
+//   q0 = (ux, uy, hx, hy)      mean in pixels; conservative half-extents of {alpha' >= 0.002}
+//   q1 = (a, b, c, alpha)      log2(g) = a dx^2 + b dx dy + c dy^2  (conic pre-scaled by
+//                              -0.5*log2e, -log2e, -0.5*log2e), opacity
+//   q2 = (r, g, b, gsid bits)
+struct __align__(16) Rec {
+  float4 q0, q1, q2;
+};
+static_assert(sizeof(Rec) == 48, "record must be 48 bytes");
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// alpha' of one record at one pixel -- THE single definition used by forward and backward
+// so both take identical skip decisions (kernel.cu:243-246 / :909-913).
+// Returns g = exp(-maha/2) through *g.
+__device__ __forceinline__ float alpha_prime(const float4 &q1, float dx, float dy, float *g) {
+  float t = fmaf(q1.y, dy, q1.x * dx);
+  float p = fmaf(t, dx, (q1.z * dy) * dy);
+  p = fminf(p, 0.0f);  // max(0, maha)
+  float gg = ex2_approx(p);
+  *g = gg;
+  return fminf(ALPHA_CLAMP, q1.w * gg);
+}
+
+// ---- mbarrier + bulk async copy (global -> shared), single-CTA forms
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+// 1-D TMA: bytes must be a multiple of 16, both addresses 16-B aligned.
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes,
+                                         uint64_t *bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+          "r"(smem_u32(dst_smem)),
+      "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+}  // namespace gsb
+
+#define GSB_CUDA_TRY(expr)                                 \
+  do {                                                     \
+    cudaError_t _e = (expr);                               \
+    if (_e != cudaSuccess) return gsb::set_cuda_error(_e, #expr, __FILE__, __LINE__); \
+  } while (0)
+
+namespace gsb {
+int set_cuda_error(cudaError_t e, const char *what, const char *file, int line);
+int set_arg_error(const char *msg);
+}  // namespace gsb

@@ -1,0 +1,66 @@
+// Internal launcher prototypes (host side, C++).  The public surface is include/gsplat_b200.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace gsb {
+
+struct Rec;
+
+// ---- launch accounting / optional per-kernel CUDA-event timing (api.cu).  Every launcher
+// opens a ProfScope; the launch counter always runs, events are recorded only while
+// gsb_profile_enable(1) is in effect (bench.py's roofline leg).
+enum KernelId {
+  K_PROJECT = 0, K_COV3D, K_COV2D, K_SH2COLOR, K_INVCOV, K_RECTS, K_SCAN, K_KEYS, K_SORT, K_RANGES,
+  K_PACK, K_DRAW, K_DRAW_BWD, K_COUNT
+};
+struct ProfScope {
+  ProfScope(int id, cudaStream_t st);
+  ~ProfScope();
+  int id_;
+  cudaStream_t st_;
+  cudaEvent_t stop_;
+};
+
+int launch_project(int N, const float *pws, const float *Rcw, const float *tcw, float fx, float fy,
+                   float cx, float cy, float *us, float *pcs, float *depths, float *du_dpcs,
+                   cudaStream_t st);
+int launch_cov3d(int N, const float *rots, const float *scales, const float *depths, float *cov3ds,
+                 float *Jr, float *Js, cudaStream_t st);
+int launch_cov2d(int N, const float *cov3ds, const float *pcs, const float *Rcw, const float *depths,
+                 float fx, float fy, float width, float height, float *cov2ds, float *Jc, float *Jp,
+                 cudaStream_t st);
+int launch_sh2color(int N, int k3, const float *shs, const float *pws, const float *twc, float *colors,
+                    float *Js, float *Jp, cudaStream_t st);
+int launch_inv_cov2d(int N, const float *cov2ds, float *depths, float *cinv2ds, int32_t *areas,
+                     float *J, cudaStream_t st);
+
+// ---- binning (binning.cu)
+struct BinLayout {  // carve-up of the phase-1 workspace
+  size_t rects, counts, offsets, total, scan_tmp, scan_tmp_bytes, bytes;
+};
+BinLayout bin_layout(int N);
+int launch_bin(int H, int W, int N, const float *us, float *depths, int32_t *areas, void *ws,
+               const BinLayout &L, cudaStream_t st);
+
+struct SortLayout {  // carve-up of the phase-2 workspace
+  size_t keys_a, keys_b, vals_a, recs, sort_tmp, sort_tmp_bytes, bytes;
+};
+int sort_layout(int N, int H, int W, int64_t P, SortLayout *out);
+int launch_sort_and_pack(int H, int W, int N, int64_t P, const float *us, const float *cinv2ds,
+                         const float *alphas, const float *depths, const float *colors,
+                         const void *bin_ws, const BinLayout &BL, void *ws, const SortLayout &SL,
+                         int32_t *ranges, int32_t *gsid_per_patch, cudaStream_t st);
+int launch_pack_only(int64_t P, const int32_t *gsid_per_patch, const float *us, const float *cinv2ds,
+                     const float *alphas, const float *colors, Rec *recs, cudaStream_t st);
+
+// ---- rasterizer (raster_fwd.cu / raster_bwd.cu)
+int launch_draw(int H, int W, const int32_t *ranges, const Rec *recs, float *image, int32_t *contrib,
+                float *final_tau, cudaStream_t st);
+int launch_draw_backward(int H, int W, const int32_t *ranges, const Rec *recs, const int32_t *contrib,
+                         const float *final_tau, const float *dloss_dgammas, float *dloss_dus,
+                         float *dloss_dcinv2ds, float *dloss_dalphas, float *dloss_dcolors,
+                         cudaStream_t st);
+
+}  // namespace gsb

@@ -1,0 +1,62 @@
+"""Host-side mirror of the reference's autograd wrapper (gsplat/gsmodel.py:6-93).
+
+`GSFunction.apply(pws, shs, alphas, scales, rots, us, cam)` has the reference's argument
+order, return values (image, depths > 0.2 mask) and gradient slots, and drives the same
+seven operators in the same order, so it is the caller contract the parity and benchmark
+harnesses exercise on the GPU box (where the reference tree itself is not available).
+The reference's own gsplat/gsmodel.py runs unmodified on top of `gsplatcu` as well.
+"""
+import torch
+
+from . import ops as gsc
+
+
+class Camera:
+    """Fields of gsplat/gausplat_dataset.py:14-27 that the rasterizer reads."""
+
+    def __init__(self, width, height, fx, fy, cx, cy, Rcw, tcw, twc=None):
+        self.width, self.height = int(width), int(height)
+        self.fx, self.fy, self.cx, self.cy = float(fx), float(fy), float(cx), float(cy)
+        self.Rcw, self.tcw = Rcw, tcw
+        self.twc = twc if twc is not None else -torch.linalg.inv(Rcw) @ tcw
+
+
+class GSFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pws, shs, alphas, scales, rots, us, cam):
+        us, pcs, depths, du_dpcs = gsc.project(pws, cam.Rcw, cam.tcw, cam.fx, cam.fy, cam.cx, cam.cy, True)
+        cov3ds, dcov3d_drots, dcov3d_dscales = gsc.computeCov3D(rots, scales, depths, True)
+        cov2ds, dcov2d_dcov3ds, dcov2d_dpcs = gsc.computeCov2D(
+            cov3ds, pcs, cam.Rcw, depths, cam.fx, cam.fy, cam.width, cam.height, True)
+        colors, dcolor_dshs, dcolor_dpws = gsc.sh2Color(shs, pws, cam.twc, True)
+        cinv2ds, areas, dcinv2d_dcov2ds = gsc.inverseCov2D(cov2ds, depths, True)
+        image, contrib, final_tau, patch_range_per_tile, gsid_per_patch = gsc.splat(
+            cam.height, cam.width, us, cinv2ds, alphas, depths, colors, areas)
+        ctx.cam = cam
+        ctx.alpha_shape = alphas.shape
+        ctx.save_for_backward(us, cinv2ds, alphas, depths, colors, contrib, final_tau,
+                              patch_range_per_tile, gsid_per_patch, dcinv2d_dcov2ds, dcov2d_dcov3ds,
+                              dcov3d_drots, dcov3d_dscales, dcolor_dshs, du_dpcs, dcov2d_dpcs,
+                              dcolor_dpws)
+        return image, depths > 0.2
+
+    @staticmethod
+    def backward(ctx, dloss_dgammas, _):
+        cam = ctx.cam
+        (us, cinv2ds, alphas, depths, colors, contrib, final_tau, patch_range_per_tile,
+         gsid_per_patch, dcinv2d_dcov2ds, dcov2d_dcov3ds, dcov3d_drots, dcov3d_dscales, dcolor_dshs,
+         du_dpcs, dcov2d_dpcs, dcolor_dpws) = ctx.saved_tensors
+        dloss_dus, dloss_dcinv2ds, dloss_dalphas, dloss_dcolors = gsc.splatB(
+            cam.height, cam.width, us, cinv2ds, alphas, depths, colors, contrib, final_tau,
+            patch_range_per_tile, gsid_per_patch, dloss_dgammas)
+        # docs/backward.md eq. (3)-(7): chain through the saved per-Gaussian Jacobians
+        R = cam.Rcw
+        dloss_dcov2ds = dloss_dcinv2ds @ dcinv2d_dcov2ds
+        dloss_dcov3ds = dloss_dcov2ds @ dcov2d_dcov3ds
+        dloss_drots = dloss_dcov3ds @ dcov3d_drots
+        dloss_dscales = dloss_dcov3ds @ dcov3d_dscales
+        n = dloss_dcolors.shape[0]
+        dloss_dshs = (dloss_dcolors.transpose(1, 2) @ dcolor_dshs).transpose(1, 2).reshape(n, -1)
+        dloss_dpws = (dloss_dus @ du_dpcs + dloss_dcov2ds @ dcov2d_dpcs) @ R + dloss_dcolors @ dcolor_dpws
+        return (dloss_dpws.squeeze(1), dloss_dshs, dloss_dalphas.reshape(ctx.alpha_shape), dloss_dscales.squeeze(1),
+                dloss_drots.squeeze(1), dloss_dus.squeeze(1), None)

@@ -1,0 +1,232 @@
+"""The reference's `gsplatcu` operator surface on top of the C ABI (include/gsplat_b200.h).
+
+Seven functions with the reference's positional signatures, return arity, shapes, dtypes
+and in-place side effects (gsplatcu/ext.cpp:10-76, gsplatcu/gausplat.cu): `project`,
+`computeCov3D`, `computeCov2D`, `sh2Color`, `inverseCov2D`, `splat`, `splatB`.
+torch is used for device memory and the current stream only; all compute is in
+libgsplat_b200.so.  Differences from the reference, all deliberate:
+  * dtype / device / shape are checked and violations raise (the reference checks nothing);
+  * work is enqueued on torch's current stream and nothing device-synchronises except the
+    one read of the patch count inside `splat` (the reference syncs the device after every
+    kernel, common.cuh:17-25);
+  * N == 0 and P <= 1 are handled (SURVEY 8b "degenerate inputs").
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+
+_lib_handle = None
+
+
+def _L():
+    global _lib_handle
+    if _lib_handle is None:
+        _lib_handle = _lib.load()
+    return _lib_handle
+
+
+def _chk(t, name, dtype=torch.float32, last=None, ndim=None):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError("%s must be a torch.Tensor" % name)
+    if not t.is_cuda:
+        raise ValueError("%s must be a CUDA tensor (there is no CPU path)" % name)
+    if t.dtype != dtype:
+        raise TypeError("%s must be %s, got %s" % (name, dtype, t.dtype))
+    if ndim is not None and t.dim() != ndim:
+        raise ValueError("%s must have %d dims, got shape %s" % (name, ndim, tuple(t.shape)))
+    if last is not None and (t.dim() == 0 or t.shape[-1] != last):
+        raise ValueError("%s must have last dim %d, got shape %s" % (name, last, tuple(t.shape)))
+    return t.contiguous()
+
+
+def _same_device(ref, *ts):
+    for t in ts:
+        if t.device != ref.device:
+            raise ValueError("all tensors must be on the same device")
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def project(pws, Rcw, tcw, focal_x, focal_y, center_x, center_y, calc_J):
+    """ext.cpp:54-61.  -> [us[N,2], pcs[N,3], depths[N]] (+ du_dpcs[N,2,3] if calc_J)"""
+    pws = _chk(pws, "pws", last=3, ndim=2)
+    Rcw = _chk(Rcw, "Rcw"); tcw = _chk(tcw, "tcw")
+    if Rcw.numel() != 9 or tcw.numel() != 3:
+        raise ValueError("Rcw must have 9 and tcw 3 elements")
+    _same_device(pws, Rcw, tcw)
+    N = pws.shape[0]
+    o = dict(dtype=torch.float32, device=pws.device)
+    us = torch.empty((N, 2), **o); pcs = torch.empty((N, 3), **o); depths = torch.empty((N,), **o)
+    J = torch.empty((N, 2, 3), **o) if calc_J else None
+    lib = _L()
+    with torch.cuda.device(pws.device):
+        _lib.check(lib.gsb_project(N, _ptr(pws), _ptr(Rcw), _ptr(tcw), float(focal_x), float(focal_y),
+                                   float(center_x), float(center_y), _ptr(us), _ptr(pcs), _ptr(depths),
+                                   _ptr(J), _stream()), lib)
+    return [us, pcs, depths, J] if calc_J else [us, pcs, depths]
+
+
+def computeCov3D(rots, scales, depths, calc_J):
+    """ext.cpp:39-42.  -> [cov3ds[N,6]] (+ dcov3d_drots[N,6,4], dcov3d_dscales[N,6,3])"""
+    rots = _chk(rots, "rots", last=4, ndim=2); scales = _chk(scales, "scales", last=3, ndim=2)
+    depths = _chk(depths, "depths")
+    _same_device(rots, scales, depths)
+    N = rots.shape[0]
+    if scales.shape[0] != N or depths.numel() != N:
+        raise ValueError("rots, scales, depths disagree on N")
+    o = dict(dtype=torch.float32, device=rots.device)
+    cov = torch.empty((N, 6), **o)
+    Jr = torch.empty((N, 6, 4), **o) if calc_J else None
+    Js = torch.empty((N, 6, 3), **o) if calc_J else None
+    lib = _L()
+    with torch.cuda.device(rots.device):
+        _lib.check(lib.gsb_compute_cov3d(N, _ptr(rots), _ptr(scales), _ptr(depths), _ptr(cov), _ptr(Jr),
+                                         _ptr(Js), _stream()), lib)
+    return [cov, Jr, Js] if calc_J else [cov]
+
+
+def computeCov2D(cov3ds, pcs, Rcw, depths, focal_x, focal_y, width, height, calc_J):
+    """ext.cpp:44-52.  -> [cov2ds[N,3]] (+ dcov2d_dcov3ds[N,3,6], dcov2d_dpcs[N,3,3])"""
+    cov3ds = _chk(cov3ds, "cov3ds", last=6, ndim=2); pcs = _chk(pcs, "pcs", last=3, ndim=2)
+    Rcw = _chk(Rcw, "Rcw"); depths = _chk(depths, "depths")
+    _same_device(pcs, cov3ds, Rcw, depths)
+    N = pcs.shape[0]
+    if cov3ds.shape[0] != N or depths.numel() != N or Rcw.numel() != 9:
+        raise ValueError("cov3ds, pcs, depths disagree on N (or Rcw is not 3x3)")
+    o = dict(dtype=torch.float32, device=pcs.device)
+    cov = torch.empty((N, 3), **o)
+    Jc = torch.empty((N, 3, 6), **o) if calc_J else None
+    Jp = torch.empty((N, 3, 3), **o) if calc_J else None
+    lib = _L()
+    with torch.cuda.device(pcs.device):
+        _lib.check(lib.gsb_compute_cov2d(N, _ptr(cov3ds), _ptr(pcs), _ptr(Rcw), _ptr(depths),
+                                         float(focal_x), float(focal_y), float(width), float(height),
+                                         _ptr(cov), _ptr(Jc), _ptr(Jp), _stream()), lib)
+    return [cov, Jc, Jp] if calc_J else [cov]
+
+
+def sh2Color(shs, pws, twc, calc_J):
+    """ext.cpp:63-66.  shs[N,3k], k in {1,4,9,16}.
+    -> [colors[N,3]] (+ dcolor_dshs[N,1,k], dcolor_dpws[N,3,3])"""
+    shs = _chk(shs, "shs", ndim=2); pws = _chk(pws, "pws", last=3, ndim=2); twc = _chk(twc, "twc")
+    _same_device(pws, shs, twc)
+    N = pws.shape[0]
+    if shs.shape[0] != N or shs.shape[1] % 3 != 0 or shs.shape[1] // 3 not in (1, 4, 9, 16):
+        raise ValueError("shs must be [N, 3k] with k in {1,4,9,16}, got %s" % (tuple(shs.shape),))
+    if twc.numel() != 3:
+        raise ValueError("twc must have 3 elements")
+    k = shs.shape[1] // 3
+    o = dict(dtype=torch.float32, device=pws.device)
+    col = torch.empty((N, 3), **o)
+    Js = torch.empty((N, 1, k), **o) if calc_J else None
+    Jp = torch.empty((N, 3, 3), **o) if calc_J else None
+    lib = _L()
+    with torch.cuda.device(pws.device):
+        _lib.check(lib.gsb_sh2color(N, k, _ptr(shs), _ptr(pws), _ptr(twc), _ptr(col), _ptr(Js), _ptr(Jp),
+                                    _stream()), lib)
+    return [col, Js, Jp] if calc_J else [col]
+
+
+def inverseCov2D(cov2ds, depths, calc_J):
+    """ext.cpp:34-36.  MUTATES depths (NaN determinant -> -1, kernel.cu:301-305).
+    -> [cinv2ds[N,3], areas[N,2] int32] (+ dcinv2d_dcov2ds[N,3,3])"""
+    cov2ds = _chk(cov2ds, "cov2ds", last=3, ndim=2); depths = _chk(depths, "depths")
+    _same_device(cov2ds, depths)
+    N = cov2ds.shape[0]
+    if depths.numel() != N:
+        raise ValueError("cov2ds and depths disagree on N")
+    o = dict(dtype=torch.float32, device=cov2ds.device)
+    cinv = torch.empty((N, 3), **o)
+    areas = torch.empty((N, 2), dtype=torch.int32, device=cov2ds.device)
+    J = torch.empty((N, 3, 3), **o) if calc_J else None
+    lib = _L()
+    with torch.cuda.device(cov2ds.device):
+        _lib.check(lib.gsb_inverse_cov2d(N, _ptr(cov2ds), _ptr(depths), _ptr(cinv), _ptr(areas), _ptr(J),
+                                         _stream()), lib)
+    return [cinv, areas, J] if calc_J else [cinv, areas]
+
+
+def splat(height, width, us, cinv2ds, alphas, depths, colors, areas):
+    """ext.cpp:10-18.  MUTATES depths / areas for Gaussians that touch no tile
+    (kernel.cu:114-119).  -> [image[3,H,W], contrib[H,W] i32, final_tau[H,W],
+    patch_range_per_tile[T,2] i32, gsid_per_patch[P] i32]"""
+    H, W = int(height), int(width)
+    if H <= 0 or W <= 0:
+        raise ValueError("height and width must be positive")
+    us = _chk(us, "us", last=2, ndim=2); cinv2ds = _chk(cinv2ds, "cinv2ds", last=3, ndim=2)
+    alphas = _chk(alphas, "alphas"); depths = _chk(depths, "depths")
+    colors = _chk(colors, "colors", last=3, ndim=2)
+    areas = _chk(areas, "areas", dtype=torch.int32, last=2, ndim=2)
+    _same_device(us, cinv2ds, alphas, depths, colors, areas)
+    N = us.shape[0]
+    if not (cinv2ds.shape[0] == N and alphas.numel() == N and depths.numel() == N
+            and colors.shape[0] == N and areas.shape[0] == N):
+        raise ValueError("splat inputs disagree on N")
+    dev = us.device
+    T = ((W + 15) // 16) * ((H + 15) // 16)
+    lib = _L()
+    with torch.cuda.device(dev):
+        st = _stream()
+        bin_bytes = lib.gsb_splat_bin_workspace_bytes(N)
+        bin_ws = torch.empty((bin_bytes,), dtype=torch.uint8, device=dev)
+        P = C.c_int64(0)
+        _lib.check(lib.gsb_splat_bin(H, W, N, _ptr(us), _ptr(depths), _ptr(areas), _ptr(bin_ws), bin_bytes,
+                                     C.byref(P), st), lib)
+        P = int(P.value)
+        ws_bytes = lib.gsb_splat_workspace_bytes(N, H, W, P)
+        ws = torch.empty((max(ws_bytes, 1),), dtype=torch.uint8, device=dev)
+        image = torch.empty((3, H, W), dtype=torch.float32, device=dev)
+        contrib = torch.empty((H, W), dtype=torch.int32, device=dev)
+        final_tau = torch.empty((H, W), dtype=torch.float32, device=dev)
+        ranges = torch.empty((T, 2), dtype=torch.int32, device=dev)
+        gsid = torch.empty((P,), dtype=torch.int32, device=dev)
+        _lib.check(lib.gsb_splat_render(H, W, N, P, _ptr(us), _ptr(cinv2ds), _ptr(alphas), _ptr(depths),
+                                        _ptr(colors), _ptr(bin_ws), _ptr(ws), ws_bytes, _ptr(image),
+                                        _ptr(contrib), _ptr(final_tau), _ptr(ranges), _ptr(gsid), st), lib)
+        # the workspaces are consumed by kernels already enqueued on `st`; the caching
+        # allocator only reuses them for later work on the same stream
+    return [image, contrib, final_tau, ranges, gsid]
+
+
+def splatB(height, width, us, cinv2ds, alphas, depths, colors, contrib, final_tau,
+           patch_range_per_tile, gsid_per_patch, dloss_dgammas):
+    """ext.cpp:20-32.  -> [dloss_dus[N,1,2], dloss_dcinv2ds[N,1,3], dloss_dalphas[N,1,1],
+    dloss_dcolors[N,1,3]]   (`depths` is accepted and unused, as in the reference)"""
+    H, W = int(height), int(width)
+    us = _chk(us, "us", last=2, ndim=2); cinv2ds = _chk(cinv2ds, "cinv2ds", last=3, ndim=2)
+    alphas = _chk(alphas, "alphas"); colors = _chk(colors, "colors", last=3, ndim=2)
+    contrib = _chk(contrib, "contrib", dtype=torch.int32); final_tau = _chk(final_tau, "final_tau")
+    ranges = _chk(patch_range_per_tile, "patch_range_per_tile", dtype=torch.int32, last=2)
+    gsid = _chk(gsid_per_patch, "gsid_per_patch", dtype=torch.int32)
+    dl = _chk(dloss_dgammas, "dloss_dgammas")
+    _same_device(us, cinv2ds, alphas, colors, contrib, final_tau, ranges, gsid, dl)
+    N = us.shape[0]
+    T = ((W + 15) // 16) * ((H + 15) // 16)
+    if contrib.numel() != H * W or final_tau.numel() != H * W or dl.numel() != 3 * H * W:
+        raise ValueError("contrib / final_tau / dloss_dgammas do not match height x width")
+    if ranges.shape[0] != T:
+        raise ValueError("patch_range_per_tile does not match the tile grid")
+    if not (cinv2ds.shape[0] == N and alphas.numel() == N and colors.shape[0] == N):
+        raise ValueError("splatB inputs disagree on N")
+    P = gsid.numel()
+    dev = us.device
+    o = dict(dtype=torch.float32, device=dev)
+    du = torch.empty((N, 1, 2), **o); dc = torch.empty((N, 1, 3), **o)
+    da = torch.empty((N, 1, 1), **o); dcol = torch.empty((N, 1, 3), **o)
+    lib = _L()
+    with torch.cuda.device(dev):
+        ws_bytes = lib.gsb_splat_backward_workspace_bytes(N, H, W, P)
+        ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+        _lib.check(lib.gsb_splat_backward(H, W, N, P, _ptr(us), _ptr(cinv2ds), _ptr(alphas), _ptr(colors),
+                                          _ptr(contrib), _ptr(final_tau), _ptr(ranges), _ptr(gsid), _ptr(dl),
+                                          _ptr(ws), ws_bytes, _ptr(du), _ptr(dc), _ptr(da), _ptr(dcol),
+                                          _stream()), lib)
+    return [du, dc, da, dcol]

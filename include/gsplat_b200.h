@@ -1,0 +1,129 @@
+/*
+ * gsplat_b200.h -- C ABI of the B200-native differentiable 3DGS rasterizer.
+ *
+ * This is the drop-in boundary for the hot path of scomup/EasyGaussianSplatting: the seven
+ * operators its pybind11 module `gsplatcu` exports (reference gsplatcu/ext.cpp:68-76, host
+ * launchers gsplatcu/gausplat.cu).  The reference has no C ABI of its own -- its boundary
+ * is `std::vector<torch::Tensor> f(torch::Tensor...)` -- so each entry point below is what
+ * a maintainer would call from those launchers instead of the `<<<>>>` launches
+ * (INTEGRATION.md shows the binding).  The Python package `gsplatcu/` in this repository
+ * binds them with ctypes and reproduces the reference's Python operator surface.
+ *
+ * Conventions (all entry points):
+ *   - plain C, no torch / C++ types; every pointer is a DEVICE pointer unless the name ends
+ *     in `_host`; tensors are dense row-major float32 (int32 where stated);
+ *   - caller owns every buffer, including workspaces (sizes from the *_workspace_bytes
+ *     queries); nothing is allocated or freed inside;
+ *   - stream-ordered on `stream` (a cudaStream_t passed as void*); no device-wide sync.
+ *     The only host synchronisation is gsb_splat_bin's wait for the patch count P;
+ *   - return 0 on success, non-zero (a cudaError_t value, or -1 for argument errors)
+ *     otherwise; gsb_last_error() returns a thread-local description;
+ *   - N == 0 / P == 0 are valid and produce empty / zero outputs (the reference reads out
+ *     of bounds for N == 0, gausplat.cu:67, and drops the image for P == 1,
+ *     kernel.cu:140-143; both are handled here).
+ *   - "culled" Gaussians (depths[i] < 0.2) get all-zero outputs, exactly what the
+ *     reference's zero-filled tensors hold for them.
+ */
+#ifndef GSPLAT_B200_H_
+#define GSPLAT_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GSB_ABI_VERSION 1
+#define GSB_TILE 16            /* reference common.cuh:13 BLOCK */
+#define GSB_RECORD_BYTES 48    /* packed per-patch record, see DESIGN.md "data layout" */
+
+typedef void *gsb_stream_t; /* cudaStream_t */
+
+int gsb_abi_version(void);
+const char *gsb_last_error(void);
+
+/* F.1.1/F.1.2/B.1.2.  Replaces `project` (ext.cpp:54-61, gausplat.cu:253-296, kernel.cu:553-617).
+ * pws[N,3], Rcw[3,3], tcw[3] -> us[N,2], pcs[N,3], depths[N] (-1 where z < 0.2),
+ * du_dpcs[N,2,3] (nullable = calc_J false). */
+int gsb_project(int N, const float *pws, const float *Rcw, const float *tcw, float fx, float fy,
+                float cx, float cy, float *us, float *pcs, float *depths, float *du_dpcs,
+                gsb_stream_t stream);
+
+/* F.2/B.2.  Replaces `computeCov3D` (ext.cpp:39-42, gausplat.cu:162-199, kernel.cu:326-423).
+ * rots[N,4] (w,x,y,z; used un-normalised), scales[N,3], depths[N] -> cov3ds[N,6] (upper
+ * triangle), dcov3d_drots[N,6,4], dcov3d_dscales[N,6,3] (both nullable together). */
+int gsb_compute_cov3d(int N, const float *rots, const float *scales, const float *depths,
+                      float *cov3ds, float *dcov3d_drots, float *dcov3d_dscales,
+                      gsb_stream_t stream);
+
+/* F.3/B.3.  Replaces `computeCov2D` (ext.cpp:44-52, gausplat.cu:201-251, kernel.cu:425-551).
+ * width/height only feed the +-1.3*tan_fov clamp.  -> cov2ds[N,3], dcov2d_dcov3ds[N,3,6],
+ * dcov2d_dpcs[N,3,3] (nullable together). */
+int gsb_compute_cov2d(int N, const float *cov3ds, const float *pcs, const float *Rcw,
+                      const float *depths, float fx, float fy, float width, float height,
+                      float *cov2ds, float *dcov2d_dcov3ds, float *dcov2d_dpcs,
+                      gsb_stream_t stream);
+
+/* F.4.  Replaces `sh2Color` (ext.cpp:63-66, gausplat.cu:298-338, kernel.cu:619-807).
+ * shs[N,3*k] laid out [coef][rgb], k = sh_dim3 in {1,4,9,16}; not gated by depth.
+ * -> colors[N,3], dcolor_dshs[N,1,k], dcolor_dpws[N,3,3] (nullable together). */
+int gsb_sh2color(int N, int sh_dim3, const float *shs, const float *pws, const float *twc,
+                 float *colors, float *dcolor_dshs, float *dcolor_dpws, gsb_stream_t stream);
+
+/* F.5.3/B.5.3.  Replaces `inverseCov2D` (ext.cpp:34-36, gausplat.cu:340-373, kernel.cu:274-324).
+ * depths is READ-WRITE: a NaN 1/det sets depths[i] = -1.  -> cinv2ds[N,3], areas[N,2] int32,
+ * dcinv2d_dcov2ds[N,3,3] (nullable). */
+int gsb_inverse_cov2d(int N, const float *cov2ds, float *depths, float *cinv2ds, int32_t *areas,
+                      float *dcinv2d_dcov2ds, gsb_stream_t stream);
+
+/* ---- splat, phase 1: tile rectangles + patch count.
+ * Replaces getRects + thrust::inclusive_scan + the D2H read of the total
+ * (gausplat.cu:54-67, kernel.cu:82-122).  depths and areas are READ-WRITE (Gaussians that
+ * touch no tile get depths = -1, areas = 0).  Leaves rects/offsets in `bin_ws` for phase 2.
+ * Writes the patch count to *P_host after synchronising `stream` (the one host sync). */
+size_t gsb_splat_bin_workspace_bytes(int N);
+int gsb_splat_bin(int H, int W, int N, const float *us, float *depths, int32_t *areas,
+                  void *bin_ws, size_t bin_ws_bytes, int64_t *P_host, gsb_stream_t stream);
+
+/* ---- splat, phase 2: keys, duplicate-key radix sort, tile ranges, record packing, draw.
+ * Replaces createKeys + thrust::sort_by_key + getRanges + draw (gausplat.cu:69-105,
+ * kernel.cu:46-80,125-271).  `alphas` is [N] (or [N,1]).  Outputs: image[3,H,W] planar,
+ * contrib[H,W] int32, final_tau[H,W], patch_range_per_tile[T,2] int32 (T = tiles),
+ * gsid_per_patch[P] int32 (Gaussian id of every patch in (tile, depth-mm, id) order).
+ * Every output element is written (no pre-zeroing needed). */
+size_t gsb_splat_workspace_bytes(int N, int H, int W, int64_t P);
+int gsb_splat_render(int H, int W, int N, int64_t P, const float *us, const float *cinv2ds,
+                     const float *alphas, const float *depths, const float *colors,
+                     const void *bin_ws, void *ws, size_t ws_bytes, float *image,
+                     int32_t *contrib, float *final_tau, int32_t *patch_range_per_tile,
+                     int32_t *gsid_per_patch, gsb_stream_t stream);
+
+/* ---- splatB.  Replaces `splatB` (ext.cpp:20-32, gausplat.cu:114-159, kernel.cu:809-950).
+ * Consumes the forward's contrib / final_tau / patch_range_per_tile / gsid_per_patch.
+ * -> dloss_dus[N,1,2], dloss_dcinv2ds[N,1,3], dloss_dalphas[N,1,1], dloss_dcolors[N,1,3]
+ * (zeroed inside). */
+size_t gsb_splat_backward_workspace_bytes(int N, int H, int W, int64_t P);
+int gsb_splat_backward(int H, int W, int N, int64_t P, const float *us, const float *cinv2ds,
+                       const float *alphas, const float *colors, const int32_t *contrib,
+                       const float *final_tau, const int32_t *patch_range_per_tile,
+                       const int32_t *gsid_per_patch, const float *dloss_dgammas, void *ws,
+                       size_t ws_bytes, float *dloss_dus, float *dloss_dcinv2ds,
+                       float *dloss_dalphas, float *dloss_dcolors, gsb_stream_t stream);
+
+/* ---- launch accounting and optional per-kernel timing (no reference counterpart; used by
+ * bench.py for `gpu_launches` and the roofline's live CUDA-event kernel durations).
+ * Kernel ids 0..gsb_profile_kernels()-1, names from gsb_profile_kernel_name().
+ * gsb_profile_launches(id) counts launches since load (id < 0: all kernels).
+ * While enabled, every kernel launch is bracketed by two events on its stream;
+ * gsb_profile_read() waits for them, returns the summed duration and clears the list. */
+void gsb_profile_enable(int on);
+int gsb_profile_kernels(void);
+const char *gsb_profile_kernel_name(int id);
+long long gsb_profile_launches(int id);
+int gsb_profile_read(int id, double *ms_total, long long *timed_launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GSPLAT_B200_H_ */

@@ -168,12 +168,21 @@ def forward_cpu_splat(height, width, us, cinv2d, alpha, depth, color, areas):
 # ---------------------------------------------------------------- full chain (fp64)
 def chain_backward(Rcw, dloss_dus, dloss_dcinv2ds, dloss_dalphas, dloss_dcolors,
                    du_dpcs, dcov3d_drots, dcov3d_dscales, dcov2d_dcov3ds, dcov2d_dpcs,
-                   dcolor_dshs, dcolor_dpws, dcinv2d_dcov2ds):
+                   dcolor_dshs, dcolor_dpws, dcinv2d_dcov2ds, use_numpy=False):
     """gsmodel.py:72-85 == backward_cpu.py:476-484: the Jacobian chain from the four splatB
     grads to parameter grads, in fp64.  Returns dict(pws, shs, alphas, scales, rots, us)."""
-    R = np.asarray(Rcw, dtype=np.float64)
-    f = lambda a: np.asarray(a, dtype=np.float64)
+    R = np.ascontiguousarray(Rcw, dtype=np.float64)
+    f = lambda a: np.ascontiguousarray(a, dtype=np.float64)
     dus, dci, dal, dco = f(dloss_dus), f(dloss_dcinv2ds), f(dloss_dalphas), f(dloss_dcolors)
+    if not use_numpy:  # one C pass (orc_chain); the numpy form below is its cross-check
+        N, k = dus.shape[0], np.asarray(dcolor_dshs).shape[-1]
+        Js = [f(a) for a in (du_dpcs, dcov3d_drots, dcov3d_dscales, dcov2d_dcov3ds, dcov2d_dpcs,
+                             dcolor_dshs, dcolor_dpws, dcinv2d_dcov2ds)]
+        dpws = np.empty((N, 3)); dshs = np.empty((N, 3 * k)); dsc = np.empty((N, 3)); dro = np.empty((N, 4))
+        lib().orc_chain(N, k, _p(R), _p(dus), _p(dci), _p(dal), _p(dco), *[_p(a) for a in Js],
+                        _p(dpws), _p(dshs), _p(dsc), _p(dro))
+        return dict(pws=dpws, shs=dshs, alphas=dal.reshape(N, 1), scales=dsc, rots=dro,
+                    us=dus.reshape(N, 2))
     dcov2d = dci @ f(dcinv2d_dcov2ds)
     dcov3d = dcov2d @ f(dcov2d_dcov3ds)
     drots = dcov3d @ f(dcov3d_drots)

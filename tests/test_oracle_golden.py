@@ -158,6 +158,10 @@ def test_full_chain_matches_backward(bl):
     du, dc, da, dcol = orc.splat_backward(H, W, f32(us), f32(cinv), bl["alphas"], f32(col),
                                           fwd, f32(dl))
     g = orc.chain_backward(bl["Rcw"], du, dc, da, dcol, du_dpcs, J3r, J3s, J2c, J2p, Jcs, Jcp, Jci)
+    g_np = orc.chain_backward(bl["Rcw"], du, dc, da, dcol, du_dpcs, J3r, J3s, J2c, J2p, Jcs, Jcp, Jci,
+                              use_numpy=True)
+    for name in g:  # C chain (orc_chain) == numpy transcription of gsmodel.py:72-85
+        close(g[name], g_np[name].reshape(g[name].shape), 1e-12 * max(1.0, np.abs(g_np[name]).max()))
     for name, ref in (("rots", "chain_drots"), ("scales", "chain_dscales"), ("shs", "chain_dshs"),
                       ("alphas", "chain_dalphas"), ("pws", "chain_dpws")):
         scale = max(1e-12, np.max(np.abs(bl[ref])))
