@@ -8,8 +8,6 @@ The reference's own gsplat/gsmodel.py runs unmodified on top of `gsplatcu` as we
 """
 import torch
 
-from . import ops as gsc
-
 
 class Camera:
     """Fields of gsplat/gausplat_dataset.py:14-27 that the rasterizer reads."""
@@ -21,9 +19,26 @@ class Camera:
         self.twc = twc if twc is not None else -torch.linalg.inv(Rcw) @ tcw
 
 
-class GSFunction(torch.autograd.Function):
+def build_gsfunction(gsc):
+    """Binds the wrapper to an operator module exposing the seven `gsplatcu` functions: ours
+    (easygaussiansplatting_b200.ops) or, in benchmarks/compare_ref_gpu.py, the reference's own
+    compiled extension -- the same harness drives both (SURVEY 8d "apples-to-apples")."""
+
+    class GSFunction(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, pws, shs, alphas, scales, rots, us, cam):
+            return _forward(gsc, ctx, pws, shs, alphas, scales, rots, us, cam)
+
+        @staticmethod
+        def backward(ctx, dloss_dgammas, _):
+            return _backward(gsc, ctx, dloss_dgammas)
+
+    return GSFunction
+
+
+class _Impl:
     @staticmethod
-    def forward(ctx, pws, shs, alphas, scales, rots, us, cam):
+    def forward(gsc, ctx, pws, shs, alphas, scales, rots, us, cam):
         us, pcs, depths, du_dpcs = gsc.project(pws, cam.Rcw, cam.tcw, cam.fx, cam.fy, cam.cx, cam.cy, True)
         cov3ds, dcov3d_drots, dcov3d_dscales = gsc.computeCov3D(rots, scales, depths, True)
         cov2ds, dcov2d_dcov3ds, dcov2d_dpcs = gsc.computeCov2D(
@@ -41,7 +56,7 @@ class GSFunction(torch.autograd.Function):
         return image, depths > 0.2
 
     @staticmethod
-    def backward(ctx, dloss_dgammas, _):
+    def backward(gsc, ctx, dloss_dgammas):
         cam = ctx.cam
         (us, cinv2ds, alphas, depths, colors, contrib, final_tau, patch_range_per_tile,
          gsid_per_patch, dcinv2d_dcov2ds, dcov2d_dcov3ds, dcov3d_drots, dcov3d_dscales, dcolor_dshs,
@@ -60,3 +75,15 @@ class GSFunction(torch.autograd.Function):
         dloss_dpws = (dloss_dus @ du_dpcs + dloss_dcov2ds @ dcov2d_dpcs) @ R + dloss_dcolors @ dcolor_dpws
         return (dloss_dpws.squeeze(1), dloss_dshs, dloss_dalphas.reshape(ctx.alpha_shape), dloss_dscales.squeeze(1),
                 dloss_drots.squeeze(1), dloss_dus.squeeze(1), None)
+
+
+_forward, _backward = _Impl.forward, _Impl.backward
+
+
+def __getattr__(name):
+    if name == "GSFunction":  # bound lazily so importing this module does not load the library
+        from . import ops
+        cls = build_gsfunction(ops)
+        globals()["GSFunction"] = cls
+        return cls
+    raise AttributeError(name)

@@ -139,19 +139,23 @@ def splat(height, width, us, cinv2ds, alphas, depths, colors, areas, margin=2e-5
                 keys=keys, ambiguous=amb.astype(bool), P=int(P))
 
 
-def splat_backward(height, width, us, cinv2ds, alphas, colors, fwd, dloss_dgammas):
+def splat_backward(height, width, us, cinv2ds, alphas, colors, fwd, dloss_dgammas,
+                   return_ambiguous=False, margin=2e-5):
     """kernel.cu:809-950 on the oracle's own forward state `fwd` (dict from splat()).
-    -> dloss_dus[N,1,2], dloss_dcinv2ds[N,1,3], dloss_dalphas[N,1,1], dloss_dcolors[N,1,3]"""
+    -> dloss_dus[N,1,2], dloss_dcinv2ds[N,1,3], dloss_dalphas[N,1,1], dloss_dcolors[N,1,3]
+    (+ bool[N]: Gaussians with a replayed alpha' within `margin` of the 0.002 threshold)"""
     us, cinv2ds, colors = _f32(us), _f32(cinv2ds), _f32(colors)
     alphas = _f32(alphas).reshape(-1)
     dl = _f32(dloss_dgammas)
     N = us.shape[0]
     du = np.empty((N, 1, 2)); dc = np.empty((N, 1, 3)); da = np.empty((N, 1, 1))
     dcol = np.empty((N, 1, 3))
+    amb = np.zeros(max(N, 1), dtype=np.uint8)[:N]
     lib().orc_drawB(int(height), int(width), N, _p(fwd["ranges"]), _p(fwd["gsid"]), _p(us),
                     _p(cinv2ds), _p(alphas), _p(colors), _p(fwd["final_tau"]),
-                    _p(fwd["contrib"]), _p(dl), _p(du), _p(dc), _p(da), _p(dcol))
-    return du, dc, da, dcol
+                    _p(fwd["contrib"]), _p(dl), _p(du), _p(dc), _p(da), _p(dcol), _p(amb),
+                    C.c_double(margin))
+    return (du, dc, da, dcol, amb.astype(bool)) if return_ambiguous else (du, dc, da, dcol)
 
 
 def forward_cpu_splat(height, width, us, cinv2d, alpha, depth, color, areas):

@@ -191,12 +191,18 @@ def run_splat_case(N, W, H, sh_dim=3, seed=0, check_bwd=True, sc=None):
     dl = upstream_gradient(W, H, seed) * (3.0 * W * H)  # O(1) upstream gradient
     grads = g.splatB(H, W, o["us"], o["cinv2ds"], alphas, o["depths"], o["colors"], contrib, ftau, ranges, gsid,
                      t(dl))
-    refg = orc.splat_backward(H, W, us, cinv, sc["alphas"], col, ref, dl)
+    *refg, amb_gs = orc.splat_backward(H, W, us, cinv, sc["alphas"], col, ref, dl, return_ambiguous=True)
+    # Gaussians with a replayed alpha' within 2e-5 of the 0.002 skip threshold may take the
+    # other branch in fp32, which moves their own gradient by one whole pixel term (the conic
+    # term carries dx^2): bounded separately and counted.
+    assert amb_gs.mean() <= 0.01, "too many threshold-ambiguous Gaussians: %g" % amb_gs.mean()
     for got, want, name in zip(grads, refg, ("dloss_dus", "dloss_dcinv2ds", "dloss_dalphas", "dloss_dcolors")):
         assert tuple(got.shape) == want.shape, name
-        e = np.abs(n(got).astype(np.float64) - want).max(initial=0)
+        err = np.abs(n(got).astype(np.float64) - want).reshape(len(want), -1).max(axis=1)
         s = np.abs(want).max(initial=1e-30)
-        assert e / s <= 1e-4, "%s: normalised max err %.3e" % (name, e / s)
+        assert err[~amb_gs].max(initial=0) / s <= 1e-4, "%s: normalised max err %.3e" % (
+            name, err[~amb_gs].max() / s)
+        assert err.max(initial=0) / s <= 5e-3, "%s: ambiguous-Gaussian err %.3e" % (name, err.max() / s)
     return sc, o, (image, contrib, ftau, ranges, gsid), ref
 
 
