@@ -124,6 +124,11 @@ def main():
         out["ours_vs_ref_normalised_max_diff"] = par
     else:
         out["note"] = "baseline/_ref/gsplatcu*.so missing: reference arm skipped"
+    for arm in arms:  # the raw tensors are scratch (hundreds of MB)
+        for k in list(out[arm]):
+            f = a.out + "." + arm + ".json." + k + ".npz"
+            if os.path.exists(f):
+                os.remove(f)
     json.dump(out, open(a.out + ".json", "w"), indent=1)
     print(json.dumps(out, indent=1))
 
