@@ -1,14 +1,17 @@
 #!/usr/bin/env python
 """bench.py -- BASELINE.json metric: rendered Mpixels/s forward+backward @ 1M Gaussians, 1080p.
 
-A "step" is one pass of the hot path over one synthetic view: the five per-Gaussian operators
-(with Jacobians, as training calls them), splat, splatB and the Jacobian chain to parameter
-gradients, driven through the `gsplatcu` operator surface by the GSFunction mirror
-(easygaussiansplatting_b200/gsfunction.py == reference gsplat/gsmodel.py:6-93).
+A "step" is one pass of the hot path over one synthetic view: parameters -> image ->
+(given dL/dimage) -> gradients of every Gaussian parameter.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
 ours, N == 1   config[1] of BASELINE.json: 1M synthetic Gaussians, 1920x1080, SH degree 3.
+               `value`/`e2e` time the fused path (GSFunctionFused: gsb_preprocess_forward,
+               splat, splatB, gsb_preprocess_backward -- every kernel ours).  The same step
+               through the reference's seven-operator surface + its torch.bmm Jacobian chain
+               (GSFunction mirror of gsplat/gsmodel.py:6-93) is reported beside it as
+               `op_surface` (that is what the unmodified reference scripts exercise).
 ours, N  > 1   multi-view data parallel: the same shared Gaussians, one camera per
                rank per step, NCCL all-reduce (sum) of the parameter gradients; weak scaling
                in views, value = total pixels of all ranks / max-over-ranks time.
@@ -17,6 +20,7 @@ reference      the CPU restatement of the reference algorithm (oracle/, OpenMP, 
 Prints ONE JSON line (rank 0).
 """
 import argparse
+import ctypes as C
 import json
 import os
 import statistics
@@ -47,8 +51,8 @@ def peaks():
 def cpu_sample(steps=1, warmup=0):
     """forward + backward of the reference algorithm on the host: per-Gaussian stages with
     Jacobians, tile binning + sort, per-pixel compositing, its backward and the Jacobian chain,
-    on rows [476,604) of the 1080p view of the 1M-Gaussian scene.  Returns (Mpix/s, sec/step,
-    threads, dict of oracle results for the GPU cross-check)."""
+    rendering rows [476,604) of the 1080p view (a 1920x128 camera with cy shifted) of the
+    1M-Gaussian scene.  Returns (Mpix/s, sec/step, threads, dict with the scene)."""
     from oracle import oracle as orc
     from easygaussiansplatting_b200.scene import synthetic_scene, upstream_gradient
     sc = synthetic_scene(N_GAUSS, WIDTH, HEIGHT, sh_dim=SH_DIM, seed=0)
@@ -56,7 +60,7 @@ def cpu_sample(steps=1, warmup=0):
     cy = sc["cy"] - CROP_Y0
     dl = upstream_gradient(WIDTH, HEIGHT, 0)[:, CROP_Y0:CROP_Y0 + CROP_ROWS, :].copy() * (3.0 * WIDTH * HEIGHT)
     f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32)
-    times, out = [], None
+    times = []
     for it in range(warmup + steps):
         t0 = time.perf_counter()
         us, pcs, depths, Ju = orc.project(sc["pws"], sc["Rcw"], sc["tcw"], sc["fx"], sc["fy"], sc["cx"], cy)
@@ -67,28 +71,32 @@ def cpu_sample(steps=1, warmup=0):
         ci, areas, Jci = orc.inverse_cov2d(f32(c2), d32)
         fwd = orc.splat(H, W, f32(us), f32(ci), sc["alphas"], d32, f32(col), areas)
         g4 = orc.splat_backward(H, W, f32(us), f32(ci), sc["alphas"], f32(col), fwd, dl)
-        grads = orc.chain_backward(sc["Rcw"], *g4, Ju, J3r, J3s, J2c, J2p, Jcs, Jcp, Jci)
+        orc.chain_backward(sc["Rcw"], *g4, Ju, J3r, J3s, J2c, J2p, Jcs, Jcp, Jci)
         dt = time.perf_counter() - t0
         if it >= warmup:
             times.append(dt)
-        out = dict(fwd=fwd, grads=grads, scene=sc, cy=cy, dl=dl)
     sec = statistics.median(times)
-    return W * H / sec / 1e6, sec, orc.num_threads(), out
+    return W * H / sec / 1e6, sec, orc.num_threads(), dict(scene=sc, cy=cy, dl=dl)
+
+
+def sample_text(sec=None):
+    s = ("rows %d-%d of the 1920x1080 view (%dx%d px, %.1f%% of the frame), all 1M Gaussians, fwd+bwd"
+         % (CROP_Y0, CROP_Y0 + CROP_ROWS, WIDTH, CROP_ROWS, 100.0 * CROP_ROWS / HEIGHT))
+    return s + (", %.1f s per pass" % sec if sec is not None else "")
 
 
 def run_reference(args, rank):
     if rank != 0:
         return
     mpix, sec, threads, _ = cpu_sample(steps=max(1, args.steps), warmup=min(1, args.warmup))
-    sample = ("rows %d-%d of the 1920x1080 view (%dx%d px, %.1f%% of the frame), all 1M Gaussians, fwd+bwd"
-              % (CROP_Y0, CROP_Y0 + CROP_ROWS, WIDTH, CROP_ROWS, 100.0 * CROP_ROWS / HEIGHT))
     line = {
         "impl": "reference", "metric": METRIC, "value": mpix, "unit": "Mpixels/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "config2: 1M synthetic Gaussians, 1920x1080, SH deg 3, fwd+bwd (CPU: bounded crop)",
                    "gaussians": N_GAUSS, "width": WIDTH, "height": HEIGHT, "sh_dim": SH_DIM},
-        "cpu_baseline": {"value": mpix, "unit": "Mpixels/s", "cores": threads, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": mpix, "unit": "Mpixels/s", "cores": threads, "kind": "port",
+                         "sample": sample_text(sec)},
         "e2e": {"value": mpix, "unit": "Mpixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -107,9 +115,10 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
+            time.sleep(0.3)
         except Exception:
             self.proc = None
 
@@ -120,22 +129,22 @@ class ClockSampler:
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.1)
         self.proc.terminate()
-        sm, mx, reasons = [], None, set()
+        sm, mx, reasons, pw = [], None, set(), []
         for ln in self.lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
             try:
-                sm.append(float(f[1])); mx = float(f[2])
+                sm.append(float(f[1])); mx = float(f[2]); pw.append(float(f[3]))
             except ValueError:
                 continue
             for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
                 if val.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "power_w_max": max(pw) if pw else None}
 
 
 # ------------------------------------------------------------------ our arm
@@ -143,7 +152,8 @@ def run_ours(args, rank, world):
     import torch
     import torch.distributed as dist
     from easygaussiansplatting_b200 import _lib
-    from easygaussiansplatting_b200.gsfunction import Camera, GSFunction
+    from easygaussiansplatting_b200.gsfunction import Camera, GSFunction, GSFunctionFused
+    from easygaussiansplatting_b200.parallel import allreduce_grads
     from easygaussiansplatting_b200.scene import ring_camera, synthetic_scene, upstream_gradient
 
     local = int(os.environ.get("LOCAL_RANK", 0))
@@ -166,27 +176,30 @@ def run_ours(args, rank, world):
     leaves = [params["pws"], params["shs"], alphas, params["scales"], params["rots"]]
     dl_host = torch.from_numpy(upstream_gradient(WIDTH, HEIGHT, rank) * (3.0 * WIDTH * HEIGHT)).pin_memory()
     dl_dev = dl_host.to(dev)
-    cam_host = torch.from_numpy(np.concatenate([Rcw.reshape(-1), tcw, twc]).astype(np.float32)).pin_memory()
+    cam_host = torch.from_numpy(np.concatenate([np.asarray(Rcw).reshape(-1), tcw, twc]).astype(np.float32)).pin_memory()
     cam_dev = torch.empty(15, device=dev)
     img_host = torch.empty((3, HEIGHT, WIDTH), dtype=torch.float32).pin_memory()
     chk_host = torch.empty(1, dtype=torch.float32).pin_memory()
 
-    def step(dl):
-        for p in leaves:
-            p.grad = None
-        image, _ = GSFunction.apply(params["pws"], params["shs"], alphas, params["scales"], params["rots"], us0, cam)
-        image.backward(dl)
-        if world > 1:  # multi-view DP: sum the parameter gradients over the views
-            flat = torch.cat([p.grad.reshape(-1) for p in leaves])
-            dist.all_reduce(flat)
-        return image
+    def make_step(F):
+        def step(dl):
+            for p in leaves:
+                p.grad = None
+            image, _ = F.apply(params["pws"], params["shs"], alphas, params["scales"], params["rots"], us0, cam)
+            image.backward(dl)
+            if world > 1:  # multi-view DP: sum the parameter gradients over the views
+                allreduce_grads([p.grad for p in leaves])
+            return image
+        return step
+
+    step_fused, step_ops = make_step(GSFunctionFused), make_step(GSFunction)
 
     def step_e2e():
         # host -> device: this view's camera and dL/dimage; device -> host: image + a gradient checksum
         cam_dev.copy_(cam_host, non_blocking=True)
         cam.Rcw, cam.tcw, cam.twc = cam_dev[:9].view(3, 3), cam_dev[9:12], cam_dev[12:15]
         dl_dev.copy_(dl_host, non_blocking=True)
-        image = step(dl_dev)
+        image = step_fused(dl_dev)
         img_host.copy_(image.detach(), non_blocking=True)
         chk_host.copy_(params["pws"].grad.abs().sum().reshape(1), non_blocking=True)
 
@@ -214,22 +227,26 @@ def run_ours(args, rank, world):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        step_fused(dl_dev)
+    torch.cuda.synchronize()
     launches0 = lib.gsb_profile_launches(-1)
-    ms_dev = timed(lambda: step(dl_dev), args.steps, args.warmup)
+    ms_dev = timed(lambda: step_fused(dl_dev), args.steps, 0)
     launches = lib.gsb_profile_launches(-1) - launches0
-    launches_timed = launches * args.steps // (args.steps + args.warmup)
     clocks = sampler.stop() if rank == 0 else None
-    ms_e2e = timed(step_e2e, args.steps, max(1, args.warmup // 2))
+    ms_e2e = timed(step_e2e, args.steps, max(3, args.warmup // 2))
+    cam.Rcw, cam.tcw, cam.twc = T(Rcw), T(tcw), T(twc)
+    ms_ops = timed(lambda: step_ops(dl_dev), max(3, args.steps // 2), 3)
+    ops_steps = max(3, args.steps // 2)
     pix = WIDTH * HEIGHT * world
     value = pix * args.steps / (ms_dev * 1e-3) / 1e6
     e2e = pix * args.steps / (ms_e2e * 1e-3) / 1e6
 
     # ---- per-kernel durations with CUDA events on the launch stream (roofline leg)
-    import ctypes as C
     prof_steps = 5
     lib.gsb_profile_enable(1)
     for _ in range(prof_steps):
-        image = step(dl_dev)
+        step_fused(dl_dev)
     torch.cuda.synchronize()
     lib.gsb_profile_enable(0)
     kern = {}
@@ -244,21 +261,18 @@ def run_ours(args, rank, world):
         return
 
     # ---- algorithmic bytes of the dominant kernel (SURVEY 8d / BASELINE.md 3)
+    from easygaussiansplatting_b200 import ops
     with torch.no_grad():
-        import gsplatcu as gsc
-        us, pcs, depths = gsc.project(params["pws"], cam.Rcw, cam.tcw, cam.fx, cam.fy, cam.cx, cam.cy, False)
-        c3 = gsc.computeCov3D(params["rots"], params["scales"], depths, False)[0]
-        c2 = gsc.computeCov2D(c3, pcs, cam.Rcw, depths, cam.fx, cam.fy, WIDTH, HEIGHT, False)[0]
-        col = gsc.sh2Color(params["shs"], params["pws"], cam.twc, False)[0]
-        ci, areas = gsc.inverseCov2D(c2, depths, False)
-        img, contrib, ftau, ranges, gsid = gsc.splat(HEIGHT, WIDTH, us, ci, alphas, depths, col, areas)
+        us, ci, col, depths, areas = ops.preprocess(params["pws"], params["rots"], params["scales"], params["shs"],
+                                                    cam.Rcw, cam.tcw, cam.twc, cam.fx, cam.fy, cam.cx, cam.cy,
+                                                    WIDTH, HEIGHT)
+        img, contrib, ftau, ranges, gsid = ops.splat(HEIGHT, WIDTH, us, ci, alphas, depths, col, areas)
         P = gsid.numel()
         gy, gx = (HEIGHT + 15) // 16, (WIDTH + 15) // 16
         pad = torch.zeros((gy * 16, gx * 16), dtype=torch.int32, device=dev)
         pad[:HEIGHT, :WIDTH] = contrib
         p_eff = int(pad.view(gy, 16, gx, 16).amax(dim=(1, 3)).sum().item())
-    Tn = gx * gy
-    WH = WIDTH * HEIGHT
+    Tn, WH = gx * gy, WIDTH * HEIGHT
     alg = {"draw_backward": 44 * p_eff + 8 * Tn + 20 * WH + 36 * N_GAUSS,
            "draw": 44 * p_eff + 8 * Tn + 20 * WH}
     top = max(kern, key=kern.get)
@@ -268,33 +282,39 @@ def run_ours(args, rank, world):
     roofline = {"bound": "hbm", "kernel": roof_k, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg[roof_k], "kernel_ms": kern[roof_k],
-                "note": "draw/draw_backward are FP32/MUFU-issue bound on dense scenes (SURVEY 8d); "
-                        "see profiles/ for pipe utilisation"}
+                "note": "draw/draw_backward are issue-bound on dense scenes (SURVEY 8d: ~140 flop/B); "
+                        "profiles/ holds the ncu pipe utilisation and dram__bytes"}
 
-    # ---- CPU baseline + gradient error vs CPU on the same crop
+    # ---- CPU baseline + gradient error vs the CPU oracle on the same crop
     cpu_mpix, cpu_sec, cpu_threads, cpu = cpu_sample(steps=1, warmup=0)
-    grad_err = gpu_vs_cpu_crop(torch, dev, cpu)
+    err = gpu_vs_cpu_crop(torch, dev, cpu)
     line = {
         "metric": METRIC, "value": value, "unit": "Mpixels/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "config2: 1M synthetic Gaussians, 1920x1080, SH deg 3, fwd+bwd through the "
-                               "gsplatcu operator surface (calc_J=True) + Jacobian chain",
+        "config": {"workload": "config2: 1M synthetic Gaussians, 1920x1080, SH deg 3, forward+backward to "
+                               "parameter gradients (fused preprocess fwd/bwd + splat + splatB)",
                    "gaussians": N_GAUSS, "width": WIDTH, "height": HEIGHT, "sh_dim": SH_DIM, "patches": P,
                    "p_eff": p_eff, "views_per_step": world,
-                   "parallelism": "1 view/rank, shared Gaussians, NCCL all-reduce of param grads" if world > 1 else "single GPU",
-                   "l2": "per-step working set ~1.5 GB (Jacobians + SH + records) >> 126 MB L2; no explicit flush"},
+                   "parallelism": ("1 view/rank, shared Gaussians, NCCL all-reduce of param grads"
+                                   if world > 1 else "single GPU"),
+                   "l2": "per-step working set (params+grads 0.47 GB, records 0.12 GB, sort buffers) > 126 MB L2; "
+                         "no explicit flush"},
         "gaussians_per_s": N_GAUSS * world * args.steps / (ms_dev * 1e-3),
-        "grad_max_rel_err_vs_cpu": grad_err,
+        "op_surface": {"what": "same step through the reference's 7-op surface (calc_J=True) + torch.bmm "
+                               "Jacobian chain (GSFunction mirror of gsmodel.py:6-93)",
+                       "value": pix * ops_steps / (ms_ops * 1e-3) / 1e6, "unit": "Mpixels/s",
+                       "ms_per_step": ms_ops / ops_steps},
+        "grad_max_rel_err_vs_cpu": err["grad_max_rel_err"], "parity_vs_cpu": err,
         "roofline": roofline,
         "kernel_ms_per_step": kern,
         "cpu_baseline": {"value": cpu_mpix, "unit": "Mpixels/s", "cores": cpu_threads, "kind": "port",
-                         "sample": "rows %d-%d of the 1080p view (%dx%d px), all 1M Gaussians, fwd+bwd, %.1f s"
-                                   % (CROP_Y0, CROP_Y0 + CROP_ROWS, WIDTH, CROP_ROWS, cpu_sec)},
+                         "sample": sample_text(cpu_sec)},
         "e2e": {"value": e2e, "unit": "Mpixels/s", "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": int(dl_host.numel() * 4 + cam_host.numel() * 4),
-                "d2h_bytes_per_step": int(img_host.numel() * 4 + 4)},
-        "gpu_launches": int(launches_timed),
+                "d2h_bytes_per_step": int(img_host.numel() * 4 + 4),
+                "what": "camera + dL/dimage from pinned host memory each step; image + gradient checksum back"},
+        "gpu_launches": int(launches),
         "clocks": clocks,
     }
     print(json.dumps(line))
@@ -303,23 +323,53 @@ def run_ours(args, rank, world):
 
 
 def gpu_vs_cpu_crop(torch, dev, cpu):
-    """max over parameter tensors of max|g_gpu - g_cpu| / max|g_cpu| on the CPU sample crop"""
-    from easygaussiansplatting_b200.gsfunction import Camera, GSFunction
+    """GPU vs CPU oracle on the CPU-sample crop (1920x128 view of the 1M scene).
+    splat / splatB are compared on the GPU's own fp32 op inputs (what the operator actually
+    received); Gaussians whose alpha' comes within 2e-5 of the 0.002 threshold at some pixel are
+    reported separately (an fp32 kernel may take the other branch there).  The per-Gaussian
+    backward is compared with the fp64 Jacobian chain on the same upstream gradients."""
+    from oracle import oracle as orc
+    from easygaussiansplatting_b200 import ops
     sc, cy, dl = cpu["scene"], cpu["cy"], cpu["dl"]
+    W, H = WIDTH, CROP_ROWS
     T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
-    cam = Camera(WIDTH, CROP_ROWS, sc["fx"], sc["fy"], sc["cx"], cy, T(sc["Rcw"]), T(sc["tcw"]), T(sc["twc"]))
-    P = {k: T(sc[k]).requires_grad_() for k in ("pws", "shs", "scales", "rots")}
-    al = T(sc["alphas"][:, None]).requires_grad_()
-    us0 = torch.zeros((N_GAUSS, 2), device=dev, requires_grad=True)
-    image, _ = GSFunction.apply(P["pws"], P["shs"], al, P["scales"], P["rots"], us0, cam)
-    image.backward(T(dl))
-    worst = 0.0
-    for name, got in (("pws", P["pws"].grad), ("shs", P["shs"].grad), ("scales", P["scales"].grad),
-                      ("rots", P["rots"].grad), ("alphas", al.grad)):
-        ref = cpu["grads"][name]
-        e = np.abs(got.cpu().numpy().reshape(ref.shape) - ref).max() / max(np.abs(ref).max(), 1e-30)
-        worst = max(worst, float(e))
-    return worst
+    n = lambda x: x.detach().cpu().numpy()
+    pws, rots, scales, shs = T(sc["pws"]), T(sc["rots"]), T(sc["scales"]), T(sc["shs"])
+    Rcw, tcw, twc, al = T(sc["Rcw"]), T(sc["tcw"]), T(sc["twc"]), T(sc["alphas"])
+    us, ci, col, depths, areas = ops.preprocess(pws, rots, scales, shs, Rcw, tcw, twc, sc["fx"], sc["fy"],
+                                                sc["cx"], cy, W, H)
+    d_in, a_in = n(depths).copy(), n(areas).copy()
+    image, contrib, ftau, ranges, gsid = ops.splat(H, W, us, ci, al, depths, col, areas)
+    grads = ops.splatB(H, W, us, ci, al, depths, col, contrib, ftau, ranges, gsid, T(dl))
+    gp = ops.preprocessB(pws, rots, scales, shs, Rcw, tcw, twc, sc["fx"], sc["fy"], sc["cx"], cy, W, H,
+                         grads[0], grads[1], grads[3])
+    ref = orc.splat(H, W, n(us), n(ci), sc["alphas"], d_in, n(col), a_in)
+    *rg, amb = orc.splat_backward(H, W, n(us), n(ci), sc["alphas"], n(col), ref, dl, return_ambiguous=True)
+    okpix = ~ref["ambiguous"]
+    out = {"image_max_abs_err": float(np.abs(n(image) - ref["image"]).max(axis=0)[okpix].max()),
+           "ambiguous_pixels": int(ref["ambiguous"].sum()), "ambiguous_gaussians": int(amb.sum()),
+           "sort_order_exact": bool(np.array_equal(n(gsid), ref["gsid"]))}
+    worst, worst_amb = 0.0, 0.0
+    for got, want, name in zip(grads, rg, ("dloss_dus", "dloss_dcinv2ds", "dloss_dalphas", "dloss_dcolors")):
+        e = np.abs(n(got).astype(np.float64) - want).reshape(len(want), -1).max(axis=1) / np.abs(want).max()
+        out[name] = float(e[~amb].max())
+        worst, worst_amb = max(worst, out[name]), max(worst_amb, float(e.max()))
+    # per-Gaussian backward: fp64 Jacobian chain on the GPU's own splatB gradients
+    f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32)
+    u64, pcs, dep, Ju = orc.project(sc["pws"], sc["Rcw"], sc["tcw"], sc["fx"], sc["fy"], sc["cx"], cy)
+    d32 = f32(dep)
+    c3, J3r, J3s = orc.compute_cov3d(sc["rots"], sc["scales"], d32)
+    c2, J2c, J2p = orc.compute_cov2d(f32(c3), f32(pcs), sc["Rcw"], d32, sc["fx"], sc["fy"], W, H)
+    _, Jcs, Jcp = orc.sh2color(sc["shs"], sc["pws"], sc["twc"])
+    _, _, Jci = orc.inverse_cov2d(f32(c2), d32)
+    chain = orc.chain_backward(sc["Rcw"], n(grads[0]), n(grads[1]), n(grads[2]), n(grads[3]), Ju, J3r, J3s, J2c,
+                               J2p, Jcs, Jcp, Jci)
+    for got, name in zip(gp, ("pws", "shs", "scales", "rots")):
+        out["d" + name] = float(np.abs(n(got).astype(np.float64) - chain[name]).max() / np.abs(chain[name]).max())
+        worst = max(worst, out["d" + name])
+    out["grad_max_rel_err"] = worst
+    out["grad_max_rel_err_incl_ambiguous"] = max(worst, worst_amb)
+    return out
 
 
 def main():

@@ -17,6 +17,8 @@ SIGNATURES = {
     "gsb_compute_cov2d": (_i, [_i, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _vp, _vp, _vp, _vp]),
     "gsb_sh2color": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gsb_inverse_cov2d": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "gsb_preprocess_forward": (_i, [_i, _i] + [_vp] * 7 + [_f] * 6 + [_vp] * 6),
+    "gsb_preprocess_backward": (_i, [_i, _i] + [_vp] * 7 + [_f] * 6 + [_vp] * 8),
     "gsb_splat_bin_workspace_bytes": (_sz, [_i]),
     "gsb_splat_bin": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _sz, C.POINTER(_i64), _vp]),
     "gsb_splat_workspace_bytes": (_sz, [_i, _i, _i, _i64]),

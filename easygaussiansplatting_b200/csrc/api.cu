@@ -31,7 +31,8 @@ static std::vector<EvPair> g_events[K_COUNT];
 static std::mutex g_prof_mu;
 static const char *const g_names[K_COUNT] = {"project", "computeCov3D", "computeCov2D", "sh2Color",
                                              "inverseCov2D", "rects", "scan(cub)", "keys", "sort(cub)",
-                                             "ranges", "pack_records", "draw", "draw_backward"};
+                                             "ranges", "pack_records", "draw", "draw_backward",
+                                             "preprocess_forward", "preprocess_backward"};
 
 ProfScope::ProfScope(int id, cudaStream_t st) : id_(id), st_(st), stop_(nullptr) {
   std::lock_guard<std::mutex> lk(g_prof_mu);
@@ -140,6 +141,36 @@ int gsb_profile_read(int id, double *ms_total, long long *timed_launches) {
   *ms_total = tot;
   *timed_launches = cnt;
   return 0;
+}
+
+int gsb_preprocess_forward(int N, int sh_dim3, const float *pws, const float *rots, const float *scales,
+                           const float *shs, const float *Rcw, const float *tcw, const float *twc, float fx,
+                           float fy, float cx, float cy, float width, float height, float *us,
+                           float *cinv2ds, float *colors, float *depths, int32_t *areas, gsb_stream_t stream) {
+  GSB_REQUIRE(N >= 0, "preprocess: N < 0");
+  GSB_REQUIRE(sh_dim3 == 1 || sh_dim3 == 4 || sh_dim3 == 9 || sh_dim3 == 16,
+              "preprocess: shs.shape[1]/3 must be 1, 4, 9 or 16");
+  GSB_REQUIRE(N == 0 || (pws && rots && scales && shs && Rcw && tcw && twc && us && cinv2ds && colors &&
+                         depths && areas),
+              "preprocess: null pointer");
+  return launch_preprocess_fwd(N, sh_dim3, pws, rots, scales, shs, Rcw, tcw, twc, fx, fy, cx, cy, width, height,
+                               us, cinv2ds, colors, depths, areas, (cudaStream_t)stream);
+}
+
+int gsb_preprocess_backward(int N, int sh_dim3, const float *pws, const float *rots, const float *scales,
+                            const float *shs, const float *Rcw, const float *tcw, const float *twc, float fx,
+                            float fy, float cx, float cy, float width, float height, const float *dloss_dus,
+                            const float *dloss_dcinv2ds, const float *dloss_dcolors, float *dloss_dpws,
+                            float *dloss_dshs, float *dloss_dscales, float *dloss_drots, gsb_stream_t stream) {
+  GSB_REQUIRE(N >= 0, "preprocessB: N < 0");
+  GSB_REQUIRE(sh_dim3 == 1 || sh_dim3 == 4 || sh_dim3 == 9 || sh_dim3 == 16,
+              "preprocessB: shs.shape[1]/3 must be 1, 4, 9 or 16");
+  GSB_REQUIRE(N == 0 || (pws && rots && scales && shs && Rcw && tcw && twc && dloss_dus && dloss_dcinv2ds &&
+                         dloss_dcolors && dloss_dpws && dloss_dshs && dloss_dscales && dloss_drots),
+              "preprocessB: null pointer");
+  return launch_preprocess_bwd(N, sh_dim3, pws, rots, scales, shs, Rcw, tcw, twc, fx, fy, cx, cy, width, height,
+                               dloss_dus, dloss_dcinv2ds, dloss_dcolors, dloss_dpws, dloss_dshs, dloss_dscales,
+                               dloss_drots, (cudaStream_t)stream);
 }
 
 size_t gsb_splat_bin_workspace_bytes(int N) { return bin_layout(N).bytes; }

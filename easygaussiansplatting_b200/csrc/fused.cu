@@ -1,0 +1,183 @@
+// Fused per-Gaussian path: one forward kernel that does the work of
+// project + computeCov3D + computeCov2D + sh2Color + inverseCov2D without materialising
+// their 109 floats/Gaussian of Jacobians, and one backward kernel that recomputes the
+// intermediates and applies the vector-Jacobian products in registers (pg_fused_math.h)
+// instead of the reference's materialise -> torch.bmm chain (gsmodel.py:21-49,72-85).
+// HBM traffic: forward 232 B in / 44 B out, backward 268 B in / 232 B out per Gaussian
+// (SH degree 3), all through the coalescing shared-memory tiles of tile_io.cuh.
+#include "common.cuh"
+#include "kernels.h"
+#include "pg_fused_math.h"
+#include "tile_io.cuh"
+
+namespace gsb {
+
+__device__ __forceinline__ pg::Cam load_cam(const float *__restrict__ Rcw, const float *__restrict__ tcw,
+                                            const float *__restrict__ twc, float fx, float fy, float cx,
+                                            float cy, float tan_fovx, float tan_fovy) {
+  pg::Cam c;
+#pragma unroll
+  for (int i = 0; i < 9; i++) c.R[i] = __ldg(Rcw + i);
+#pragma unroll
+  for (int i = 0; i < 3; i++) { c.t[i] = __ldg(tcw + i); c.twc[i] = __ldg(twc + i); }
+  c.fx = fx; c.fy = fy; c.cx = cx; c.cy = cy; c.tan_fovx = tan_fovx; c.tan_fovy = tan_fovy;
+  return c;
+}
+
+#define ROWK(K) (sm + tid * TileT<K>::S)
+
+template <int K3>
+__global__ void __launch_bounds__(PG) k_preprocess_fwd(
+    int N, const float *__restrict__ pws, const float *__restrict__ rots, const float *__restrict__ scales,
+    const float *__restrict__ shs, const float *__restrict__ Rcw, const float *__restrict__ tcw,
+    const float *__restrict__ twc, float fx, float fy, float cx, float cy, float tan_fovx, float tan_fovy,
+    float *__restrict__ us, float *__restrict__ cinv2ds, float *__restrict__ colors,
+    float *__restrict__ depths, int32_t *__restrict__ areas) {
+  constexpr int KS = 3 * K3;
+  constexpr int SMF = TileT<KS>::FLOATS > TileT<4>::FLOATS ? TileT<KS>::FLOATS : TileT<4>::FLOATS;
+  __shared__ float sm[SMF];
+  const int tid = threadIdx.x;
+  const long long base = (long long)blockIdx.x * PG;
+  const int nv = min(PG, (int)(N - base));
+  const bool valid = tid < nv;
+  const pg::Cam cam = load_cam(Rcw, tcw, twc, fx, fy, cx, cy, tan_fovx, tan_fovy);
+  float pw[3] = {0.f, 0.f, 1.f}, q[4] = {1.f, 0.f, 0.f, 0.f}, s[3] = {1.f, 1.f, 1.f};
+  tile_fetch<3>(pws, base, nv, sm, tid);
+  __syncthreads();
+  if (valid) { const float *r = ROWK(3); pw[0] = r[0]; pw[1] = r[1]; pw[2] = r[2]; }
+  __syncthreads();
+  tile_fetch<3>(scales, base, nv, sm, tid);
+  __syncthreads();
+  if (valid) { const float *r = ROWK(3); s[0] = r[0]; s[1] = r[1]; s[2] = r[2]; }
+  __syncthreads();
+  tile_fetch<4>(rots, base, nv, sm, tid);
+  __syncthreads();
+  if (valid) { const float *r = ROWK(4); q[0] = r[0]; q[1] = r[1]; q[2] = r[2]; q[3] = r[3]; }
+  __syncthreads();
+  tile_fetch<KS>(shs, base, nv, sm, tid);
+  __syncthreads();
+  float u[2] = {0.f, 0.f}, conic[3] = {0.f, 0.f, 0.f}, col[3] = {0.f, 0.f, 0.f}, depth = -1.f;
+  int area[2] = {0, 0};
+  if (valid) pg::forward_one<K3>(pw, q, s, ROWK(KS), cam, u, conic, col, &depth, area);
+  __syncthreads();
+  { float *o = ROWK(2); o[0] = u[0]; o[1] = u[1]; }
+  __syncthreads();
+  tile_flush<2>(us, base, nv, sm, tid);
+  __syncthreads();
+  { float *o = ROWK(3); o[0] = conic[0]; o[1] = conic[1]; o[2] = conic[2]; }
+  __syncthreads();
+  tile_flush<3>(cinv2ds, base, nv, sm, tid);
+  __syncthreads();
+  { float *o = ROWK(3); o[0] = col[0]; o[1] = col[1]; o[2] = col[2]; }
+  __syncthreads();
+  tile_flush<3>(colors, base, nv, sm, tid);
+  __syncthreads();
+  { float *o = ROWK(2); o[0] = __int_as_float(area[0]); o[1] = __int_as_float(area[1]); }
+  __syncthreads();
+  tile_flush<2>(reinterpret_cast<float *>(areas), base, nv, sm, tid);
+  if (valid) depths[base + tid] = depth;
+}
+
+template <int K3>
+__global__ void __launch_bounds__(PG) k_preprocess_bwd(
+    int N, const float *__restrict__ pws, const float *__restrict__ rots, const float *__restrict__ scales,
+    const float *__restrict__ shs, const float *__restrict__ Rcw, const float *__restrict__ tcw,
+    const float *__restrict__ twc, float fx, float fy, float cx, float cy, float tan_fovx, float tan_fovy,
+    const float *__restrict__ g_us, const float *__restrict__ g_cinv2ds, const float *__restrict__ g_colors,
+    float *__restrict__ g_pws, float *__restrict__ g_shs, float *__restrict__ g_scales,
+    float *__restrict__ g_rots) {
+  constexpr int KS = 3 * K3;
+  constexpr int SMF = TileT<KS>::FLOATS > TileT<4>::FLOATS ? TileT<KS>::FLOATS : TileT<4>::FLOATS;
+  __shared__ float sm[SMF];
+  const int tid = threadIdx.x;
+  const long long base = (long long)blockIdx.x * PG;
+  const int nv = min(PG, (int)(N - base));
+  const bool valid = tid < nv;
+  const pg::Cam cam = load_cam(Rcw, tcw, twc, fx, fy, cx, cy, tan_fovx, tan_fovy);
+  float pw[3] = {0.f, 0.f, 1.f}, q[4] = {1.f, 0.f, 0.f, 0.f}, s[3] = {1.f, 1.f, 1.f};
+  float gu[2] = {0.f, 0.f}, gci[3] = {0.f, 0.f, 0.f}, gcol[3] = {0.f, 0.f, 0.f};
+  tile_fetch<3>(pws, base, nv, sm, tid);
+  __syncthreads();
+  if (valid) { const float *r = ROWK(3); pw[0] = r[0]; pw[1] = r[1]; pw[2] = r[2]; }
+  __syncthreads();
+  tile_fetch<3>(scales, base, nv, sm, tid);
+  __syncthreads();
+  if (valid) { const float *r = ROWK(3); s[0] = r[0]; s[1] = r[1]; s[2] = r[2]; }
+  __syncthreads();
+  tile_fetch<4>(rots, base, nv, sm, tid);
+  __syncthreads();
+  if (valid) { const float *r = ROWK(4); q[0] = r[0]; q[1] = r[1]; q[2] = r[2]; q[3] = r[3]; }
+  __syncthreads();
+  tile_fetch<2>(g_us, base, nv, sm, tid);
+  __syncthreads();
+  if (valid) { const float *r = ROWK(2); gu[0] = r[0]; gu[1] = r[1]; }
+  __syncthreads();
+  tile_fetch<3>(g_cinv2ds, base, nv, sm, tid);
+  __syncthreads();
+  if (valid) { const float *r = ROWK(3); gci[0] = r[0]; gci[1] = r[1]; gci[2] = r[2]; }
+  __syncthreads();
+  tile_fetch<3>(g_colors, base, nv, sm, tid);
+  __syncthreads();
+  if (valid) { const float *r = ROWK(3); gcol[0] = r[0]; gcol[1] = r[1]; gcol[2] = r[2]; }
+  __syncthreads();
+  tile_fetch<KS>(shs, base, nv, sm, tid);
+  __syncthreads();
+  float gpw[3] = {0.f, 0.f, 0.f}, gq[4] = {0.f, 0.f, 0.f, 0.f}, gs[3] = {0.f, 0.f, 0.f};
+  // dL/dsh overwrites the thread's own SH row in place, then the tile is flushed
+  if (valid) pg::backward_one<K3>(pw, q, s, ROWK(KS), cam, gu, gci, gcol, gpw, gq, gs, ROWK(KS));
+  __syncthreads();
+  tile_flush<KS>(g_shs, base, nv, sm, tid);
+  __syncthreads();
+  { float *o = ROWK(3); o[0] = gpw[0]; o[1] = gpw[1]; o[2] = gpw[2]; }
+  __syncthreads();
+  tile_flush<3>(g_pws, base, nv, sm, tid);
+  __syncthreads();
+  { float *o = ROWK(3); o[0] = gs[0]; o[1] = gs[1]; o[2] = gs[2]; }
+  __syncthreads();
+  tile_flush<3>(g_scales, base, nv, sm, tid);
+  __syncthreads();
+  { float *o = ROWK(4); o[0] = gq[0]; o[1] = gq[1]; o[2] = gq[2]; o[3] = gq[3]; }
+  __syncthreads();
+  tile_flush<4>(g_rots, base, nv, sm, tid);
+}
+
+#define GSB_DISPATCH_K3(k3, CALL)                                           \
+  switch (k3) {                                                             \
+    case 1: { constexpr int K3 = 1; CALL; } break;                          \
+    case 4: { constexpr int K3 = 4; CALL; } break;                          \
+    case 9: { constexpr int K3 = 9; CALL; } break;                          \
+    case 16: { constexpr int K3 = 16; CALL; } break;                        \
+    default: return set_arg_error("sh_dim3 must be 1, 4, 9 or 16");         \
+  }
+
+int launch_preprocess_fwd(int N, int k3, const float *pws, const float *rots, const float *scales,
+                          const float *shs, const float *Rcw, const float *tcw, const float *twc, float fx,
+                          float fy, float cx, float cy, float width, float height, float *us, float *cinv2ds,
+                          float *colors, float *depths, int32_t *areas, cudaStream_t st) {
+  if (N <= 0) return 0;
+  const float tfx = width / (2 * fx), tfy = height / (2 * fy);
+  const int nb = (N + PG - 1) / PG;
+  ProfScope ps(K_PRE_FWD, st);
+  GSB_DISPATCH_K3(k3, (k_preprocess_fwd<K3><<<nb, PG, 0, st>>>(N, pws, rots, scales, shs, Rcw, tcw, twc, fx, fy, cx,
+                                                                cy, tfx, tfy, us, cinv2ds, colors, depths, areas)));
+  GSB_CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int launch_preprocess_bwd(int N, int k3, const float *pws, const float *rots, const float *scales,
+                          const float *shs, const float *Rcw, const float *tcw, const float *twc, float fx,
+                          float fy, float cx, float cy, float width, float height, const float *g_us,
+                          const float *g_cinv2ds, const float *g_colors, float *g_pws, float *g_shs,
+                          float *g_scales, float *g_rots, cudaStream_t st) {
+  if (N <= 0) return 0;
+  const float tfx = width / (2 * fx), tfy = height / (2 * fy);
+  const int nb = (N + PG - 1) / PG;
+  ProfScope ps(K_PRE_BWD, st);
+  GSB_DISPATCH_K3(k3, (k_preprocess_bwd<K3><<<nb, PG, 0, st>>>(N, pws, rots, scales, shs, Rcw, tcw, twc, fx, fy, cx,
+                                                                cy, tfx, tfy, g_us, g_cinv2ds, g_colors, g_pws,
+                                                                g_shs, g_scales, g_rots)));
+  GSB_CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace gsb

@@ -13,7 +13,7 @@ struct Rec;
 // gsb_profile_enable(1) is in effect (bench.py's roofline leg).
 enum KernelId {
   K_PROJECT = 0, K_COV3D, K_COV2D, K_SH2COLOR, K_INVCOV, K_RECTS, K_SCAN, K_KEYS, K_SORT, K_RANGES,
-  K_PACK, K_DRAW, K_DRAW_BWD, K_COUNT
+  K_PACK, K_DRAW, K_DRAW_BWD, K_PRE_FWD, K_PRE_BWD, K_COUNT
 };
 struct ProfScope {
   ProfScope(int id, cudaStream_t st);
@@ -35,6 +35,17 @@ int launch_sh2color(int N, int k3, const float *shs, const float *pws, const flo
                     float *Js, float *Jp, cudaStream_t st);
 int launch_inv_cov2d(int N, const float *cov2ds, float *depths, float *cinv2ds, int32_t *areas,
                      float *J, cudaStream_t st);
+
+// ---- fused per-Gaussian path (fused.cu)
+int launch_preprocess_fwd(int N, int k3, const float *pws, const float *rots, const float *scales,
+                          const float *shs, const float *Rcw, const float *tcw, const float *twc, float fx,
+                          float fy, float cx, float cy, float width, float height, float *us, float *cinv2ds,
+                          float *colors, float *depths, int32_t *areas, cudaStream_t st);
+int launch_preprocess_bwd(int N, int k3, const float *pws, const float *rots, const float *scales,
+                          const float *shs, const float *Rcw, const float *tcw, const float *twc, float fx,
+                          float fy, float cx, float cy, float width, float height, const float *g_us,
+                          const float *g_cinv2ds, const float *g_colors, float *g_pws, float *g_shs,
+                          float *g_scales, float *g_rots, cudaStream_t st);
 
 // ---- binning (binning.cu)
 struct BinLayout {  // carve-up of the phase-1 workspace

@@ -87,3 +87,40 @@ def __getattr__(name):
         globals()["GSFunction"] = cls
         return cls
     raise AttributeError(name)
+
+
+class GSFunctionFused(torch.autograd.Function):
+    """Same call signature, outputs and gradient slots as GSFunction, but the per-Gaussian
+    stages run as one fused forward kernel and one fused backward kernel (ops.preprocess /
+    ops.preprocessB) instead of five Jacobian-materialising ops + the torch.bmm chain.
+    Swap-in: `from easygaussiansplatting_b200.gsfunction import GSFunctionFused as GSFunction`
+    in gsplat/gsmodel.py."""
+
+    @staticmethod
+    def forward(ctx, pws, shs, alphas, scales, rots, us, cam):
+        from . import ops
+        us, cinv2ds, colors, depths, areas = ops.preprocess(
+            pws, rots, scales, shs, cam.Rcw, cam.tcw, cam.twc, cam.fx, cam.fy, cam.cx, cam.cy,
+            cam.width, cam.height)
+        image, contrib, final_tau, patch_range_per_tile, gsid_per_patch = ops.splat(
+            cam.height, cam.width, us, cinv2ds, alphas, depths, colors, areas)
+        ctx.cam = cam
+        ctx.alpha_shape = alphas.shape
+        ctx.save_for_backward(pws, shs, alphas, scales, rots, us, cinv2ds, depths, colors, contrib,
+                              final_tau, patch_range_per_tile, gsid_per_patch)
+        return image, depths > 0.2
+
+    @staticmethod
+    def backward(ctx, dloss_dgammas, _):
+        from . import ops
+        cam = ctx.cam
+        (pws, shs, alphas, scales, rots, us, cinv2ds, depths, colors, contrib, final_tau,
+         patch_range_per_tile, gsid_per_patch) = ctx.saved_tensors
+        dloss_dus, dloss_dcinv2ds, dloss_dalphas, dloss_dcolors = ops.splatB(
+            cam.height, cam.width, us, cinv2ds, alphas, depths, colors, contrib, final_tau,
+            patch_range_per_tile, gsid_per_patch, dloss_dgammas)
+        dpws, dshs, dscales, drots = ops.preprocessB(
+            pws, rots, scales, shs, cam.Rcw, cam.tcw, cam.twc, cam.fx, cam.fy, cam.cx, cam.cy,
+            cam.width, cam.height, dloss_dus, dloss_dcinv2ds, dloss_dcolors)
+        return (dpws, dshs, dloss_dalphas.reshape(ctx.alpha_shape), dscales, drots,
+                dloss_dus.squeeze(1), None)

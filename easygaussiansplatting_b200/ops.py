@@ -230,3 +230,62 @@ def splatB(height, width, us, cinv2ds, alphas, depths, colors, contrib, final_ta
                                           _ptr(ws), ws_bytes, _ptr(du), _ptr(dc), _ptr(da), _ptr(dcol),
                                           _stream()), lib)
     return [du, dc, da, dcol]
+
+
+# ---------------------------------------------------------------------------------------
+# Extensions (not in the reference module): the fused per-Gaussian path, SURVEY 8f row N1.
+def preprocess(pws, rots, scales, shs, Rcw, tcw, twc, focal_x, focal_y, center_x, center_y, width, height):
+    """project + computeCov3D + computeCov2D + sh2Color + inverseCov2D (calc_J=False) in one
+    kernel.  -> [us[N,2], cinv2ds[N,3], colors[N,3], depths[N], areas[N,2] int32], ready for
+    `splat`."""
+    pws = _chk(pws, "pws", last=3, ndim=2); rots = _chk(rots, "rots", last=4, ndim=2)
+    scales = _chk(scales, "scales", last=3, ndim=2); shs = _chk(shs, "shs", ndim=2)
+    Rcw = _chk(Rcw, "Rcw"); tcw = _chk(tcw, "tcw"); twc = _chk(twc, "twc")
+    _same_device(pws, rots, scales, shs, Rcw, tcw, twc)
+    N = pws.shape[0]
+    if not (rots.shape[0] == N and scales.shape[0] == N and shs.shape[0] == N):
+        raise ValueError("preprocess inputs disagree on N")
+    if shs.shape[1] % 3 != 0 or shs.shape[1] // 3 not in (1, 4, 9, 16):
+        raise ValueError("shs must be [N, 3k] with k in {1,4,9,16}, got %s" % (tuple(shs.shape),))
+    if Rcw.numel() != 9 or tcw.numel() != 3 or twc.numel() != 3:
+        raise ValueError("Rcw must have 9, tcw and twc 3 elements")
+    k = shs.shape[1] // 3
+    o = dict(dtype=torch.float32, device=pws.device)
+    us = torch.empty((N, 2), **o); cinv = torch.empty((N, 3), **o); col = torch.empty((N, 3), **o)
+    depths = torch.empty((N,), **o); areas = torch.empty((N, 2), dtype=torch.int32, device=pws.device)
+    lib = _L()
+    with torch.cuda.device(pws.device):
+        _lib.check(lib.gsb_preprocess_forward(
+            N, k, _ptr(pws), _ptr(rots), _ptr(scales), _ptr(shs), _ptr(Rcw), _ptr(tcw), _ptr(twc),
+            float(focal_x), float(focal_y), float(center_x), float(center_y), float(width), float(height),
+            _ptr(us), _ptr(cinv), _ptr(col), _ptr(depths), _ptr(areas), _stream()), lib)
+    return [us, cinv, col, depths, areas]
+
+
+def preprocessB(pws, rots, scales, shs, Rcw, tcw, twc, focal_x, focal_y, center_x, center_y, width, height,
+                dloss_dus, dloss_dcinv2ds, dloss_dcolors):
+    """Vector-Jacobian products of the five per-Gaussian stages (== the torch.bmm chain of
+    gsmodel.py:72-85).  -> [dloss_dpws[N,3], dloss_dshs[N,3k], dloss_dscales[N,3], dloss_drots[N,4]]"""
+    pws = _chk(pws, "pws", last=3, ndim=2); rots = _chk(rots, "rots", last=4, ndim=2)
+    scales = _chk(scales, "scales", last=3, ndim=2); shs = _chk(shs, "shs", ndim=2)
+    Rcw = _chk(Rcw, "Rcw"); tcw = _chk(tcw, "tcw"); twc = _chk(twc, "twc")
+    gu = _chk(dloss_dus, "dloss_dus", last=2); gc = _chk(dloss_dcinv2ds, "dloss_dcinv2ds", last=3)
+    gcol = _chk(dloss_dcolors, "dloss_dcolors", last=3)
+    _same_device(pws, rots, scales, shs, Rcw, tcw, twc, gu, gc, gcol)
+    N = pws.shape[0]
+    if not (rots.shape[0] == N and scales.shape[0] == N and shs.shape[0] == N and gu.numel() == 2 * N
+            and gc.numel() == 3 * N and gcol.numel() == 3 * N):
+        raise ValueError("preprocessB inputs disagree on N")
+    if shs.shape[1] % 3 != 0 or shs.shape[1] // 3 not in (1, 4, 9, 16):
+        raise ValueError("shs must be [N, 3k] with k in {1,4,9,16}, got %s" % (tuple(shs.shape),))
+    k = shs.shape[1] // 3
+    o = dict(dtype=torch.float32, device=pws.device)
+    gpw = torch.empty((N, 3), **o); gsh = torch.empty((N, 3 * k), **o)
+    gs = torch.empty((N, 3), **o); gq = torch.empty((N, 4), **o)
+    lib = _L()
+    with torch.cuda.device(pws.device):
+        _lib.check(lib.gsb_preprocess_backward(
+            N, k, _ptr(pws), _ptr(rots), _ptr(scales), _ptr(shs), _ptr(Rcw), _ptr(tcw), _ptr(twc),
+            float(focal_x), float(focal_y), float(center_x), float(center_y), float(width), float(height),
+            _ptr(gu), _ptr(gc), _ptr(gcol), _ptr(gpw), _ptr(gsh), _ptr(gs), _ptr(gq), _stream()), lib)
+    return [gpw, gsh, gs, gq]

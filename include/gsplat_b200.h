@@ -77,6 +77,25 @@ int gsb_sh2color(int N, int sh_dim3, const float *shs, const float *pws, const f
 int gsb_inverse_cov2d(int N, const float *cov2ds, float *depths, float *cinv2ds, int32_t *areas,
                       float *dcinv2d_dcov2ds, gsb_stream_t stream);
 
+/* ---- fused per-Gaussian path (extension).  No single reference entry point:
+ * gsb_preprocess_forward == project + computeCov3D + computeCov2D + sh2Color + inverseCov2D
+ * with calc_J = false (gsmodel.py:21-36 without the Jacobian outputs) in one kernel, and
+ * gsb_preprocess_backward == the Jacobian chain of gsmodel.py:72-85 (torch.bmm over the saved
+ * Jacobians) as analytic vector-Jacobian products recomputed from the parameters.
+ * width/height feed the fov clamp exactly as in gsb_compute_cov2d.  Outputs of the forward
+ * feed gsb_splat_bin / gsb_splat_render unchanged; the backward consumes gsb_splat_backward's
+ * dloss_dus / dloss_dcinv2ds / dloss_dcolors (dloss_dalphas passes through untouched) and
+ * writes dloss_dpws[N,3], dloss_dshs[N,3k], dloss_dscales[N,3], dloss_drots[N,4]. */
+int gsb_preprocess_forward(int N, int sh_dim3, const float *pws, const float *rots, const float *scales,
+                           const float *shs, const float *Rcw, const float *tcw, const float *twc, float fx,
+                           float fy, float cx, float cy, float width, float height, float *us,
+                           float *cinv2ds, float *colors, float *depths, int32_t *areas, gsb_stream_t stream);
+int gsb_preprocess_backward(int N, int sh_dim3, const float *pws, const float *rots, const float *scales,
+                            const float *shs, const float *Rcw, const float *tcw, const float *twc, float fx,
+                            float fy, float cx, float cy, float width, float height, const float *dloss_dus,
+                            const float *dloss_dcinv2ds, const float *dloss_dcolors, float *dloss_dpws,
+                            float *dloss_dshs, float *dloss_dscales, float *dloss_drots, gsb_stream_t stream);
+
 /* ---- splat, phase 1: tile rectangles + patch count.
  * Replaces getRects + thrust::inclusive_scan + the D2H read of the total
  * (gausplat.cu:54-67, kernel.cu:82-122).  depths and areas are READ-WRITE (Gaussians that

@@ -1,0 +1,135 @@
+"""GPU parity of the fused per-Gaussian path (gsb_preprocess_forward / _backward and
+GSFunctionFused) against (a) the seven-operator path it replaces and (b) the CPU oracle /
+reference-generated fixtures."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as orc
+from easygaussiansplatting_b200.scene import synthetic_scene, upstream_gradient
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(__file__), "golden")
+DEV = "cuda:0"
+
+
+def t(a, dtype=torch.float32):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dtype).to(DEV)
+
+
+def n(x):
+    return x.detach().cpu().numpy()
+
+
+def scene(N, W, H, sh_dim, seed):
+    sc = synthetic_scene(N, W, H, sh_dim=sh_dim, seed=seed)
+    rng = np.random.default_rng(seed + 3)
+    idx = rng.choice(N, size=max(1, N // 50), replace=False)
+    sc["pws"][idx, 2] = rng.uniform(-1.0, 0.19, len(idx)).astype(np.float32)
+    wide = rng.choice(N, size=max(1, N // 50), replace=False)
+    sc["pws"][wide, 0] *= 6.0
+    return sc
+
+
+@pytest.mark.parametrize("N,sh_dim", [(1, 48), (129, 3), (5000, 12), (30000, 27), (100000, 48)])
+def test_preprocess_equals_five_ops(N, sh_dim):
+    import gsplatcu as g
+    from easygaussiansplatting_b200 import ops
+    W, H = 640, 360
+    sc = scene(N, W, H, sh_dim, N)
+    pws, rots, scales, shs = t(sc["pws"]), t(sc["rots"]), t(sc["scales"]), t(sc["shs"])
+    Rcw, tcw, twc = t(sc["Rcw"]), t(sc["tcw"]), t(sc["twc"])
+    us, pcs, depths = g.project(pws, Rcw, tcw, sc["fx"], sc["fy"], sc["cx"], sc["cy"], False)
+    c3 = g.computeCov3D(rots, scales, depths, False)[0]
+    c2 = g.computeCov2D(c3, pcs, Rcw, depths, sc["fx"], sc["fy"], W, H, False)[0]
+    col = g.sh2Color(shs, pws, twc, False)[0]
+    ci, areas = g.inverseCov2D(c2, depths, False)
+    fus, fci, fcol, fd, far = ops.preprocess(pws, rots, scales, shs, Rcw, tcw, twc, sc["fx"], sc["fy"], sc["cx"],
+                                             sc["cy"], W, H)
+    assert torch.equal(fd < 0, depths < 0)
+    assert torch.allclose(fus, us, rtol=1e-6, atol=1e-4) and torch.allclose(fd, depths, rtol=1e-6, atol=1e-6)
+    assert torch.allclose(fcol, col, rtol=1e-5, atol=1e-5)
+    assert torch.allclose(fci, ci, rtol=2e-4, atol=1e-6)
+    assert (far != areas).float().mean().item() < 2e-3 and (far - areas).abs().max().item() <= 1
+    assert not fus[fd < 0].any() and not fci[fd < 0].any() and not far[fd < 0].any()
+
+
+def run_both(sc, W, H, seed=0):
+    from easygaussiansplatting_b200.gsfunction import Camera, GSFunction, GSFunctionFused
+    cam = Camera(W, H, sc["fx"], sc["fy"], sc["cx"], sc["cy"], t(sc["Rcw"]), t(sc["tcw"]), t(sc["twc"]))
+    dl = t(upstream_gradient(W, H, seed) * (3.0 * W * H))
+    out = []
+    for F in (GSFunction, GSFunctionFused):
+        P = {k: t(sc[k]).requires_grad_() for k in ("pws", "shs", "scales", "rots")}
+        al = t(sc["alphas"][:, None]).requires_grad_()
+        us0 = torch.zeros((len(sc["pws"]), 2), device=DEV, requires_grad=True)
+        image, mask = F.apply(P["pws"], P["shs"], al, P["scales"], P["rots"], us0, cam)
+        image.backward(dl)
+        out.append(dict(image=image.detach(), mask=mask, pws=P["pws"].grad, shs=P["shs"].grad, alphas=al.grad,
+                        scales=P["scales"].grad, rots=P["rots"].grad, us=us0.grad))
+    return out
+
+
+@pytest.mark.parametrize("N,W,H,sh_dim", [(20000, 320, 240, 48), (3000, 250, 130, 12), (500, 64, 64, 3)])
+def test_fused_function_matches_op_surface(N, W, H, sh_dim):
+    a, b = run_both(scene(N, W, H, sh_dim, N), W, H, N)
+    assert torch.equal(a["mask"], b["mask"])
+    # a radius that flips by one between the two fp32 evaluation orders changes a tile list
+    # but not the picture beyond the alpha' < 0.002 tail
+    assert (a["image"] - b["image"]).abs().max().item() < 2e-3
+    assert (a["image"] - b["image"]).abs().mean().item() < 1e-6
+    for k in ("pws", "shs", "alphas", "scales", "rots", "us"):
+        s = a[k].abs().max().item()
+        e = (a[k] - b[k]).abs().max().item() / max(s, 1e-30)
+        assert e < 2e-3, (k, e)
+        em = (a[k] - b[k]).abs().mean().item() / max(a[k].abs().mean().item(), 1e-30)
+        assert em < 1e-4, (k, em)
+
+
+def test_fused_full_chain_golden_fixture():
+    """params -> L1 loss -> parameter grads against backward_cpu.backward() (blend.npz)"""
+    from easygaussiansplatting_b200.gsfunction import Camera, GSFunctionFused
+    bl = dict(np.load(os.path.join(G, "blend.npz")))
+    fx, fy, cx, cy, W, H = bl["cam"]
+    cam = Camera(int(W), int(H), fx, fy, cx, cy, t(bl["Rcw"]), t(bl["tcw"]), t(np.zeros(3, np.float32)))
+    P = {k: t(bl[k]).requires_grad_() for k in ("pws", "shs", "scales", "rots")}
+    alphas = t(bl["alphas"][:, None]).requires_grad_()
+    us = torch.zeros((len(bl["pws"]), 2), device=DEV, requires_grad=True)
+    image, mask = GSFunctionFused.apply(P["pws"], P["shs"], alphas, P["scales"], P["rots"], us, cam)
+    loss = torch.nn.functional.l1_loss(image, t(bl["image_gt"].transpose(2, 0, 1)))
+    loss.backward()
+    assert abs(loss.item() - float(bl["chain_loss"][0])) < 1e-5 and mask.all()
+    for name, ref in (("rots", "chain_drots"), ("scales", "chain_dscales"), ("shs", "chain_dshs"),
+                      ("pws", "chain_dpws")):
+        e = np.abs(n(P[name].grad) - bl[ref]).max() / np.abs(bl[ref]).max()
+        assert e < 1e-4, (name, e)
+    e = np.abs(n(alphas.grad) - bl["chain_dalphas"]).max() / np.abs(bl["chain_dalphas"]).max()
+    assert e < 1e-4, ("alphas", e)
+
+
+def test_preprocess_backward_vs_oracle_chain():
+    """gsb_preprocess_backward on random upstream grads vs the oracle's fp64 Jacobian chain"""
+    from easygaussiansplatting_b200 import ops
+    N, W, H, k3 = 40000, 640, 360, 16
+    sc = scene(N, W, H, 3 * k3, 7)
+    f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32)
+    us, pcs, depths, Ju = orc.project(sc["pws"], sc["Rcw"], sc["tcw"], sc["fx"], sc["fy"], sc["cx"], sc["cy"])
+    d32 = f32(depths)
+    c3, J3r, J3s = orc.compute_cov3d(sc["rots"], sc["scales"], d32)
+    c2, J2c, J2p = orc.compute_cov2d(f32(c3), f32(pcs), sc["Rcw"], d32, sc["fx"], sc["fy"], W, H)
+    col, Jcs, Jcp = orc.sh2color(sc["shs"], sc["pws"], sc["twc"])
+    ci, areas, Jci = orc.inverse_cov2d(f32(c2), d32)
+    rng = np.random.default_rng(0)
+    gu = rng.normal(size=(N, 1, 2)).astype(np.float32); gci = rng.normal(size=(N, 1, 3)).astype(np.float32)
+    gcol = rng.normal(size=(N, 1, 3)).astype(np.float32); gal = np.zeros((N, 1, 1), np.float32)
+    keep = depths > 0
+    gu[~keep] = 0; gci[~keep] = 0; gcol[~keep] = 0
+    ref = orc.chain_backward(sc["Rcw"], gu, gci, gal, gcol, Ju, J3r, J3s, J2c, J2p, Jcs, Jcp, Jci)
+    gpw, gsh, gs, gq = ops.preprocessB(t(sc["pws"]), t(sc["rots"]), t(sc["scales"]), t(sc["shs"]), t(sc["Rcw"]),
+                                       t(sc["tcw"]), t(sc["twc"]), sc["fx"], sc["fy"], sc["cx"], sc["cy"], W, H,
+                                       t(gu), t(gci), t(gcol))
+    for got, name in ((gpw, "pws"), (gsh, "shs"), (gs, "scales"), (gq, "rots")):
+        e = np.abs(n(got).astype(np.float64) - ref[name]).max() / np.abs(ref[name]).max()
+        assert e < 2e-5, (name, e)
