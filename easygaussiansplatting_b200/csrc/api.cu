@@ -32,7 +32,8 @@ static std::mutex g_prof_mu;
 static const char *const g_names[K_COUNT] = {"project", "computeCov3D", "computeCov2D", "sh2Color",
                                              "inverseCov2D", "rects", "scan(cub)", "keys", "sort(cub)",
                                              "ranges", "pack_records", "draw", "draw_backward",
-                                             "preprocess_forward", "preprocess_backward"};
+                                             "preprocess_forward", "preprocess_backward",
+                                             "finalize_splat_grads"};
 
 ProfScope::ProfScope(int id, cudaStream_t st) : id_(id), st_(st), stop_(nullptr) {
   std::lock_guard<std::mutex> lk(g_prof_mu);
@@ -223,8 +224,9 @@ int gsb_splat_render(int H, int W, int N, int64_t P, const float *us, const floa
 }
 
 size_t gsb_splat_backward_workspace_bytes(int N, int H, int W, int64_t P) {
-  (void)N; (void)H; (void)W;
-  return (size_t)(P > 0 ? P : 1) * sizeof(Rec) + 256;
+  (void)H; (void)W;
+  // packed records (256-B aligned) + the [N,9] moment accumulators
+  return (size_t)(P > 0 ? P : 1) * sizeof(Rec) + 512 + (size_t)(N > 0 ? N : 1) * 9 * sizeof(float) + 256;
 }
 
 int gsb_splat_backward(int H, int W, int N, int64_t P, const float *us, const float *cinv2ds,
@@ -236,24 +238,25 @@ int gsb_splat_backward(int H, int W, int N, int64_t P, const float *us, const fl
   GSB_REQUIRE(N >= 0 && H > 0 && W > 0 && P >= 0, "splatB: bad N/H/W/P");
   GSB_REQUIRE(N == 0 || (dloss_dus && dloss_dcinv2ds && dloss_dalphas && dloss_dcolors), "splatB: null output");
   cudaStream_t st = (cudaStream_t)stream;
-  if (N > 0) {
-    GSB_CUDA_TRY(cudaMemsetAsync(dloss_dus, 0, sizeof(float) * 2 * (size_t)N, st));
-    GSB_CUDA_TRY(cudaMemsetAsync(dloss_dcinv2ds, 0, sizeof(float) * 3 * (size_t)N, st));
-    GSB_CUDA_TRY(cudaMemsetAsync(dloss_dalphas, 0, sizeof(float) * (size_t)N, st));
-    GSB_CUDA_TRY(cudaMemsetAsync(dloss_dcolors, 0, sizeof(float) * 3 * (size_t)N, st));
-  }
-  if (P == 0 || N == 0) return 0;
-  GSB_REQUIRE(us && cinv2ds && alphas && colors && contrib && final_tau && patch_range_per_tile &&
-                  gsid_per_patch && dloss_dgammas && ws,
-              "splatB: null pointer");
+  if (N == 0) return 0;
+  GSB_REQUIRE(cinv2ds && ws, "splatB: null pointer");
   GSB_REQUIRE(ws_bytes >= gsb_splat_backward_workspace_bytes(N, H, W, P), "splatB: workspace too small");
-  // 256-B align the record stream inside the workspace (cp.async.bulk needs 16 B)
+  // workspace: [records, 256-B aligned (cp.async.bulk needs 16 B)] [moment rows]
   uintptr_t base = (reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255;
   Rec *recs = reinterpret_cast<Rec *>(base);
-  int rc = launch_pack_only(P, gsid_per_patch, us, cinv2ds, alphas, colors, recs, st);
-  if (rc) return rc;
-  return launch_draw_backward(H, W, patch_range_per_tile, recs, contrib, final_tau, dloss_dgammas, dloss_dus,
-                              dloss_dcinv2ds, dloss_dalphas, dloss_dcolors, st);
+  uintptr_t mbase = (base + (size_t)(P > 0 ? P : 1) * sizeof(Rec) + 255) & ~(uintptr_t)255;
+  float *moments = reinterpret_cast<float *>(mbase);
+  if (P > 0) {
+    GSB_REQUIRE(us && alphas && colors && contrib && final_tau && patch_range_per_tile && gsid_per_patch &&
+                    dloss_dgammas,
+                "splatB: null pointer");
+    int rc = launch_pack_only(P, gsid_per_patch, us, cinv2ds, alphas, colors, recs, st);
+    if (rc) return rc;
+  }
+  // P == 0: nothing was drawn; the zeroed moment rows finalise to all-zero gradients
+  return launch_draw_backward(H, W, N, patch_range_per_tile, P > 0 ? recs : nullptr, contrib, final_tau,
+                              dloss_dgammas, cinv2ds, moments, dloss_dus, dloss_dcinv2ds, dloss_dalphas,
+                              dloss_dcolors, st);
 }
 
 }  // extern "C"

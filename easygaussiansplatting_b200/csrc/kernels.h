@@ -13,7 +13,7 @@ struct Rec;
 // gsb_profile_enable(1) is in effect (bench.py's roofline leg).
 enum KernelId {
   K_PROJECT = 0, K_COV3D, K_COV2D, K_SH2COLOR, K_INVCOV, K_RECTS, K_SCAN, K_KEYS, K_SORT, K_RANGES,
-  K_PACK, K_DRAW, K_DRAW_BWD, K_PRE_FWD, K_PRE_BWD, K_COUNT
+  K_PACK, K_DRAW, K_DRAW_BWD, K_PRE_FWD, K_PRE_BWD, K_FINALIZE, K_COUNT
 };
 struct ProfScope {
   ProfScope(int id, cudaStream_t st);
@@ -69,9 +69,9 @@ int launch_pack_only(int64_t P, const int32_t *gsid_per_patch, const float *us, 
 // ---- rasterizer (raster_fwd.cu / raster_bwd.cu)
 int launch_draw(int H, int W, const int32_t *ranges, const Rec *recs, float *image, int32_t *contrib,
                 float *final_tau, cudaStream_t st);
-int launch_draw_backward(int H, int W, const int32_t *ranges, const Rec *recs, const int32_t *contrib,
-                         const float *final_tau, const float *dloss_dgammas, float *dloss_dus,
-                         float *dloss_dcinv2ds, float *dloss_dalphas, float *dloss_dcolors,
-                         cudaStream_t st);
+int launch_draw_backward(int H, int W, int N, const int32_t *ranges, const Rec *recs, const int32_t *contrib,
+                         const float *final_tau, const float *dloss_dgammas, const float *cinv2ds,
+                         float *moments, float *dloss_dus, float *dloss_dcinv2ds, float *dloss_dalphas,
+                         float *dloss_dcolors, cudaStream_t st);
 
 }  // namespace gsb

@@ -5,35 +5,66 @@
 // batch any pixel of the tile needs (max contrib).  Each pixel replays its saved
 // (final_tau, contrib) state: tau <- tau / (1 - alpha'), dL/dalpha' = tau (c - gamma_next) . dL/dgamma,
 // with gamma_next kept as the scalar s = dL/dgamma . gamma_next (s <- alpha' (dL/dgamma . c) + (1 - alpha') s).
-// Geometry gradients are linear in per-pixel moments, so a pixel only produces
+//
+// Geometry gradients are linear in per-pixel moments, so a pixel only produces nine numbers
 //   w dx, w dy, w dx^2, w dx dy, w dy^2   (w = dL/dalpha' * alpha'),  dL/dalpha' * g,  alpha' tau dL/dgamma_rgb
-// and the conic is applied once per (warp, record) after the warp reduction.
-// The reference issues 9 global atomics per (pixel, record); here the 32 pixels of a warp are
-// summed with shuffles first (<= 9 atomics per (warp, record)), records that cannot touch
-// the warp's rectangle are culled by the same ballot test as the forward, and records where
-// no pixel is active are skipped before any reduction.
+// which are summed over the 32 pixels of the warp with a SPLIT butterfly: at every level each
+// lane keeps half of the values and trades the other half, so the 9 sums cost 12 shuffles
+// (5+3+2+1+1) instead of 45, and end up in 9 different lanes.  Those 9 lanes then issue ONE
+// predicated red.global.add into the Gaussian's contiguous 9-float moment row (36 B, two
+// sectors) -- the reference issues 9 atomics per (pixel, record) into four arrays.
+// finalize_splat_grads() turns moment rows into the four gradient tensors:
+//   dL/du = -(A Sx + B Sy, B Sx + C Sy),  dL/dconic = (-Sxx/2, -Sxy, -Syy/2).
+// Records that cannot touch the warp's rectangle are culled by the same ballot test as the
+// forward; records where no pixel is active are skipped before any reduction.
 #include "common.cuh"
 #include "kernels.h"
+#include "tile_io.cuh"
 
 namespace gsb {
 
 constexpr int BWD_BATCH = 128;
+constexpr int MOM = 9;  // floats per moment row
 
-__device__ __forceinline__ float warp_sum(float v) {
-  v += __shfl_xor_sync(0xffffffffu, v, 16);
-  v += __shfl_xor_sync(0xffffffffu, v, 8);
-  v += __shfl_xor_sync(0xffffffffu, v, 4);
-  v += __shfl_xor_sync(0xffffffffu, v, 2);
-  v += __shfl_xor_sync(0xffffffffu, v, 1);
-  return v;
+// Sum 9 per-lane values over the warp.  Returns the total of value `slot_of_lane(lane)` in
+// every lane (lanes 2k and 2k+1 hold the same one); 12 SHFL.
+__device__ __forceinline__ float split_reduce9(const float (&v)[9], int lane) {
+  const bool u16 = lane & 16, u8 = lane & 8, u4 = lane & 4, u2 = lane & 2;
+  const unsigned F = 0xffffffffu;
+  float a[5], b[3], c[2], d;
+  // level 1: lower half keeps 0..4, upper half keeps 5..8
+#pragma unroll
+  for (int i = 0; i < 4; i++) a[i] = (u16 ? v[i + 5] : v[i]) + __shfl_xor_sync(F, u16 ? v[i] : v[i + 5], 16);
+  a[4] = (u16 ? 0.f : v[4]) + __shfl_xor_sync(F, u16 ? v[4] : 0.f, 16);
+  // level 2: keeps 0..2 | 3..4
+#pragma unroll
+  for (int i = 0; i < 2; i++) b[i] = (u8 ? a[i + 3] : a[i]) + __shfl_xor_sync(F, u8 ? a[i] : a[i + 3], 8);
+  b[2] = (u8 ? 0.f : a[2]) + __shfl_xor_sync(F, u8 ? a[2] : 0.f, 8);
+  // level 3: keeps 0..1 | 2
+  c[0] = (u4 ? b[2] : b[0]) + __shfl_xor_sync(F, u4 ? b[0] : b[2], 4);
+  c[1] = (u4 ? 0.f : b[1]) + __shfl_xor_sync(F, u4 ? b[1] : 0.f, 4);
+  // level 4: keeps 0 | 1
+  d = (u2 ? c[1] : c[0]) + __shfl_xor_sync(F, u2 ? c[0] : c[1], 2);
+  // level 5
+  d += __shfl_xor_sync(F, d, 1);
+  return d;
+}
+// which of the 9 values a lane ends up with (-1: a padding slot, or the odd twin lane)
+__device__ __forceinline__ int slot_of_lane(int lane) {
+  if (lane & 1) return -1;
+  const bool u16 = lane & 16, u8 = lane & 8, u4 = lane & 4, u2 = lane & 2;
+  int local;
+  if (!u8) local = u4 ? (u2 ? -1 : 2) : (u2 ? 1 : 0);
+  else local = u4 ? -1 : (u2 ? 4 : 3);
+  if (local < 0) return -1;
+  const int g = local + (u16 ? 5 : 0);
+  return g < MOM ? g : -1;
 }
 
 __global__ void __launch_bounds__(256) k_draw_bwd(
     int W, int H, int gx, const int2 *__restrict__ ranges, const Rec *__restrict__ recs,
     const int32_t *__restrict__ contrib, const float *__restrict__ final_tau,
-    const float *__restrict__ dloss_dgammas, float *__restrict__ dloss_dus,
-    float *__restrict__ dloss_dcinv2ds, float *__restrict__ dloss_dalphas,
-    float *__restrict__ dloss_dcolors) {
+    const float *__restrict__ dloss_dgammas, float *__restrict__ moments) {
   __shared__ Rec sbuf[2][BWD_BATCH];
   __shared__ __align__(8) uint64_t mbar[2];
   __shared__ int s_wmax[8];
@@ -87,6 +118,8 @@ __global__ void __launch_bounds__(256) k_draw_bwd(
 
   const float fpx = (float)px, fpy = (float)py;
   const float bx0 = (float)rx0, bx1 = (float)(rx0 + 7), by0 = (float)ry0, by1 = (float)(ry0 + 3);
+  const int slot = slot_of_lane(lane);
+  float *const mom_lane = moments + (slot >= 0 ? slot : 0);
   float sdot = 0.f;  // dL/dgamma . gamma_next
 
   for (int bi = 0; bi < nbn; bi++) {
@@ -129,21 +162,8 @@ __global__ void __launch_bounds__(256) k_draw_bwd(
             v[5] = dl_dap * g;
             v[6] = wc * dlr; v[7] = wc * dlg; v[8] = wc * dlb;
           }
-#pragma unroll
-          for (int i = 0; i < 9; i++) v[i] = warp_sum(v[i]);
-          if (lane == 0) {
-            const int gid = __float_as_int(q2.w);
-            const float A = q1.x * (-2.0f / LOG2E), B = q1.y * (-1.0f / LOG2E), C = q1.z * (-2.0f / LOG2E);
-            atomicAdd(dloss_dus + 2 * (size_t)gid + 0, -(A * v[0] + B * v[1]));
-            atomicAdd(dloss_dus + 2 * (size_t)gid + 1, -(B * v[0] + C * v[1]));
-            atomicAdd(dloss_dcinv2ds + 3 * (size_t)gid + 0, -0.5f * v[2]);
-            atomicAdd(dloss_dcinv2ds + 3 * (size_t)gid + 1, -v[3]);
-            atomicAdd(dloss_dcinv2ds + 3 * (size_t)gid + 2, -0.5f * v[4]);
-            atomicAdd(dloss_dalphas + gid, v[5]);
-            atomicAdd(dloss_dcolors + 3 * (size_t)gid + 0, v[6]);
-            atomicAdd(dloss_dcolors + 3 * (size_t)gid + 1, v[7]);
-            atomicAdd(dloss_dcolors + 3 * (size_t)gid + 2, v[8]);
-          }
+          const float tot = split_reduce9(v, lane);
+          if (slot >= 0) atomicAdd(mom_lane + (size_t)__float_as_int(q2.w) * MOM, tot);
         }
       }
     }
@@ -158,16 +178,64 @@ __global__ void __launch_bounds__(256) k_draw_bwd(
   }
 }
 
-int launch_draw_backward(int H, int W, const int32_t *ranges, const Rec *recs, const int32_t *contrib,
-                         const float *final_tau, const float *dloss_dgammas, float *dloss_dus,
-                         float *dloss_dcinv2ds, float *dloss_dalphas, float *dloss_dcolors,
-                         cudaStream_t st) {
+// moment rows [N,9] -> dloss_dus[N,2], dloss_dcinv2ds[N,3], dloss_dalphas[N], dloss_dcolors[N,3]
+__global__ void __launch_bounds__(PG) k_finalize_grads(int N, const float *__restrict__ moments,
+                                                       const float *__restrict__ cinv2ds,
+                                                       float *__restrict__ dus, float *__restrict__ dcinv,
+                                                       float *__restrict__ dalphas, float *__restrict__ dcolors) {
+  __shared__ float sm[TileT<MOM>::FLOATS];
+  const int tid = threadIdx.x;
+  const long long base = (long long)blockIdx.x * PG;
+  const int nv = min(PG, (int)(N - base));
+  const bool valid = tid < nv;
+  float A = 0.f, B = 0.f, Cc = 0.f, m[MOM];
+  tile_fetch<3>(cinv2ds, base, nv, sm, tid);
+  __syncthreads();
+  if (valid) { const float *r = sm + tid * TileT<3>::S; A = r[0]; B = r[1]; Cc = r[2]; }
+  __syncthreads();
+  tile_fetch<MOM>(moments, base, nv, sm, tid);
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < MOM; i++) m[i] = valid ? sm[tid * TileT<MOM>::S + i] : 0.f;
+  __syncthreads();
+  {
+    // untouched Gaussians stay exactly 0 even if their conic is inf/NaN (reference: no atomics ran)
+    const bool none = (m[0] == 0.f) && (m[1] == 0.f);
+    float *o = sm + tid * TileT<2>::S;
+    o[0] = none ? 0.f : -(A * m[0] + B * m[1]);
+    o[1] = none ? 0.f : -(B * m[0] + Cc * m[1]);
+  }
+  __syncthreads();
+  tile_flush<2>(dus, base, nv, sm, tid);
+  __syncthreads();
+  { float *o = sm + tid * TileT<3>::S; o[0] = -0.5f * m[2]; o[1] = -m[3]; o[2] = -0.5f * m[4]; }
+  __syncthreads();
+  tile_flush<3>(dcinv, base, nv, sm, tid);
+  __syncthreads();
+  { float *o = sm + tid * TileT<3>::S; o[0] = m[6]; o[1] = m[7]; o[2] = m[8]; }
+  __syncthreads();
+  tile_flush<3>(dcolors, base, nv, sm, tid);
+  if (valid) dalphas[base + tid] = m[5];
+}
+
+int launch_draw_backward(int H, int W, int N, const int32_t *ranges, const Rec *recs, const int32_t *contrib,
+                         const float *final_tau, const float *dloss_dgammas, const float *cinv2ds,
+                         float *moments, float *dloss_dus, float *dloss_dcinv2ds, float *dloss_dalphas,
+                         float *dloss_dcolors, cudaStream_t st) {
   const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
-  if (gx <= 0 || gy <= 0) return 0;
-  ProfScope ps(K_DRAW_BWD, st);
-  k_draw_bwd<<<gx * gy, 256, 0, st>>>(W, H, gx, reinterpret_cast<const int2 *>(ranges), recs, contrib,
-                                      final_tau, dloss_dgammas, dloss_dus, dloss_dcinv2ds, dloss_dalphas,
-                                      dloss_dcolors);
+  if (gx <= 0 || gy <= 0 || N <= 0) return 0;
+  GSB_CUDA_TRY(cudaMemsetAsync(moments, 0, sizeof(float) * MOM * (size_t)N, st));
+  if (recs != nullptr) {
+    ProfScope ps(K_DRAW_BWD, st);
+    k_draw_bwd<<<gx * gy, 256, 0, st>>>(W, H, gx, reinterpret_cast<const int2 *>(ranges), recs, contrib,
+                                        final_tau, dloss_dgammas, moments);
+  }
+  GSB_CUDA_TRY(cudaGetLastError());
+  {
+    ProfScope ps(K_FINALIZE, st);
+    k_finalize_grads<<<(N + PG - 1) / PG, PG, 0, st>>>(N, moments, cinv2ds, dloss_dus, dloss_dcinv2ds,
+                                                       dloss_dalphas, dloss_dcolors);
+  }
   GSB_CUDA_TRY(cudaGetLastError());
   return 0;
 }
