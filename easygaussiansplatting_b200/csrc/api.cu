@@ -177,7 +177,7 @@ int gsb_preprocess_backward(int N, int sh_dim3, const float *pws, const float *r
 size_t gsb_splat_bin_workspace_bytes(int N) { return bin_layout(N).bytes; }
 
 int gsb_splat_bin(int H, int W, int N, const float *us, float *depths, int32_t *areas, void *bin_ws,
-                  size_t bin_ws_bytes, int64_t *P_host, gsb_stream_t stream) {
+                  size_t bin_ws_bytes, int64_t *P_host, uint32_t *depth_key_max_host, gsb_stream_t stream) {
   GSB_REQUIRE(N >= 0 && H > 0 && W > 0, "splat: bad N/H/W");
   GSB_REQUIRE(P_host != nullptr && bin_ws != nullptr, "splat: null workspace / P_host");
   GSB_REQUIRE(N == 0 || (us && depths && areas), "splat: null pointer");
@@ -186,12 +186,19 @@ int gsb_splat_bin(int H, int W, int N, const float *us, float *depths, int32_t *
   cudaStream_t st = (cudaStream_t)stream;
   int rc = launch_bin(H, W, N, us, depths, areas, bin_ws, L, st);
   if (rc) return rc;
-  uint32_t total = 0;
-  GSB_CUDA_TRY(cudaMemcpyAsync(&total, static_cast<char *>(bin_ws) + L.total, sizeof(uint32_t),
+  uint32_t total[2] = {0, 0};  // [patch count, largest depth key]
+  GSB_CUDA_TRY(cudaMemcpyAsync(total, static_cast<char *>(bin_ws) + L.total, 2 * sizeof(uint32_t),
                                cudaMemcpyDeviceToHost, st));
   GSB_CUDA_TRY(cudaStreamSynchronize(st));
-  *P_host = (int64_t)total;
+  *P_host = (int64_t)total[0];
+  if (depth_key_max_host) *depth_key_max_host = total[1];
   return 0;
+}
+
+size_t gsb_splat_records_offset(int N, int H, int W, int64_t P) {
+  SortLayout L;
+  if (sort_layout(N, H, W, P, &L)) return 0;
+  return L.recs;
 }
 
 size_t gsb_splat_workspace_bytes(int N, int H, int W, int64_t P) {
@@ -200,8 +207,9 @@ size_t gsb_splat_workspace_bytes(int N, int H, int W, int64_t P) {
   return L.bytes;
 }
 
-int gsb_splat_render(int H, int W, int N, int64_t P, const float *us, const float *cinv2ds,
-                     const float *alphas, const float *depths, const float *colors, const void *bin_ws,
+int gsb_splat_render(int H, int W, int N, int64_t P, uint32_t depth_key_max, const float *us,
+                     const float *cinv2ds, const float *alphas, const float *depths, const float *colors,
+                     const void *bin_ws,
                      void *ws, size_t ws_bytes, float *image, int32_t *contrib, float *final_tau,
                      int32_t *patch_range_per_tile, int32_t *gsid_per_patch, gsb_stream_t stream) {
   GSB_REQUIRE(N >= 0 && H > 0 && W > 0 && P >= 0, "splat: bad N/H/W/P");
@@ -216,7 +224,7 @@ int gsb_splat_render(int H, int W, int N, int64_t P, const float *us, const floa
     GSB_REQUIRE(ws_bytes >= SL.bytes, "splat: workspace too small");
   }
   const BinLayout BL = bin_layout(N);
-  int rc = launch_sort_and_pack(H, W, N, P, us, cinv2ds, alphas, depths, colors, bin_ws, BL, ws, SL,
+  int rc = launch_sort_and_pack(H, W, N, P, depth_key_max, us, cinv2ds, alphas, depths, colors, bin_ws, BL, ws, SL,
                                 patch_range_per_tile, gsid_per_patch, st);
   if (rc) return rc;
   const Rec *recs = P > 0 ? reinterpret_cast<const Rec *>(static_cast<char *>(ws) + SL.recs) : nullptr;
@@ -232,26 +240,33 @@ size_t gsb_splat_backward_workspace_bytes(int N, int H, int W, int64_t P) {
 int gsb_splat_backward(int H, int W, int N, int64_t P, const float *us, const float *cinv2ds,
                        const float *alphas, const float *colors, const int32_t *contrib,
                        const float *final_tau, const int32_t *patch_range_per_tile,
-                       const int32_t *gsid_per_patch, const float *dloss_dgammas, void *ws,
-                       size_t ws_bytes, float *dloss_dus, float *dloss_dcinv2ds, float *dloss_dalphas,
+                       const int32_t *gsid_per_patch, const float *dloss_dgammas,
+                       const void *packed_records, void *ws, size_t ws_bytes, float *dloss_dus, float *dloss_dcinv2ds, float *dloss_dalphas,
                        float *dloss_dcolors, gsb_stream_t stream) {
   GSB_REQUIRE(N >= 0 && H > 0 && W > 0 && P >= 0, "splatB: bad N/H/W/P");
   GSB_REQUIRE(N == 0 || (dloss_dus && dloss_dcinv2ds && dloss_dalphas && dloss_dcolors), "splatB: null output");
   cudaStream_t st = (cudaStream_t)stream;
   if (N == 0) return 0;
   GSB_REQUIRE(cinv2ds && ws, "splatB: null pointer");
-  GSB_REQUIRE(ws_bytes >= gsb_splat_backward_workspace_bytes(N, H, W, P), "splatB: workspace too small");
+  // with the forward's records handed in, the workspace only has to hold the moment rows
+  const int64_t P_ws = packed_records != nullptr ? 0 : P;
+  GSB_REQUIRE(ws_bytes >= gsb_splat_backward_workspace_bytes(N, H, W, P_ws), "splatB: workspace too small");
   // workspace: [records, 256-B aligned (cp.async.bulk needs 16 B)] [moment rows]
   uintptr_t base = (reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255;
   Rec *recs = reinterpret_cast<Rec *>(base);
-  uintptr_t mbase = (base + (size_t)(P > 0 ? P : 1) * sizeof(Rec) + 255) & ~(uintptr_t)255;
+  uintptr_t mbase = (base + (size_t)(P_ws > 0 ? P_ws : 1) * sizeof(Rec) + 255) & ~(uintptr_t)255;
   float *moments = reinterpret_cast<float *>(mbase);
   if (P > 0) {
     GSB_REQUIRE(us && alphas && colors && contrib && final_tau && patch_range_per_tile && gsid_per_patch &&
                     dloss_dgammas,
                 "splatB: null pointer");
-    int rc = launch_pack_only(P, gsid_per_patch, us, cinv2ds, alphas, colors, recs, st);
-    if (rc) return rc;
+    if (packed_records != nullptr) {  // the forward's record stream is still valid: skip the re-pack
+      GSB_REQUIRE((reinterpret_cast<uintptr_t>(packed_records) & 15) == 0, "splatB: packed_records misaligned");
+      recs = const_cast<Rec *>(static_cast<const Rec *>(packed_records));
+    } else {
+      int rc = launch_pack_only(P, gsid_per_patch, us, cinv2ds, alphas, colors, recs, st);
+      if (rc) return rc;
+    }
   }
   // P == 0: nothing was drawn; the zeroed moment rows finalise to all-zero gradients
   return launch_draw_backward(H, W, N, patch_range_per_tile, P > 0 ? recs : nullptr, contrib, final_tau,

@@ -59,8 +59,8 @@ struct SortLayout {  // carve-up of the phase-2 workspace
   size_t keys_a, keys_b, vals_a, recs, sort_tmp, sort_tmp_bytes, bytes;
 };
 int sort_layout(int N, int H, int W, int64_t P, SortLayout *out);
-int launch_sort_and_pack(int H, int W, int N, int64_t P, const float *us, const float *cinv2ds,
-                         const float *alphas, const float *depths, const float *colors,
+int launch_sort_and_pack(int H, int W, int N, int64_t P, uint32_t depth_key_max, const float *us,
+                         const float *cinv2ds, const float *alphas, const float *depths, const float *colors,
                          const void *bin_ws, const BinLayout &BL, void *ws, const SortLayout &SL,
                          int32_t *ranges, int32_t *gsid_per_patch, cudaStream_t st);
 int launch_pack_only(int64_t P, const int32_t *gsid_per_patch, const float *us, const float *cinv2ds,

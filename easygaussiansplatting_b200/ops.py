@@ -177,9 +177,9 @@ def splat(height, width, us, cinv2ds, alphas, depths, colors, areas):
         st = _stream()
         bin_bytes = lib.gsb_splat_bin_workspace_bytes(N)
         bin_ws = torch.empty((bin_bytes,), dtype=torch.uint8, device=dev)
-        P = C.c_int64(0)
+        P, dkmax = C.c_int64(0), C.c_uint32(0)
         _lib.check(lib.gsb_splat_bin(H, W, N, _ptr(us), _ptr(depths), _ptr(areas), _ptr(bin_ws), bin_bytes,
-                                     C.byref(P), st), lib)
+                                     C.byref(P), C.byref(dkmax), st), lib)
         P = int(P.value)
         ws_bytes = lib.gsb_splat_workspace_bytes(N, H, W, P)
         ws = torch.empty((max(ws_bytes, 1),), dtype=torch.uint8, device=dev)
@@ -188,12 +188,51 @@ def splat(height, width, us, cinv2ds, alphas, depths, colors, areas):
         final_tau = torch.empty((H, W), dtype=torch.float32, device=dev)
         ranges = torch.empty((T, 2), dtype=torch.int32, device=dev)
         gsid = torch.empty((P,), dtype=torch.int32, device=dev)
-        _lib.check(lib.gsb_splat_render(H, W, N, P, _ptr(us), _ptr(cinv2ds), _ptr(alphas), _ptr(depths),
-                                        _ptr(colors), _ptr(bin_ws), _ptr(ws), ws_bytes, _ptr(image),
-                                        _ptr(contrib), _ptr(final_tau), _ptr(ranges), _ptr(gsid), st), lib)
+        _lib.check(lib.gsb_splat_render(H, W, N, P, dkmax.value, _ptr(us), _ptr(cinv2ds), _ptr(alphas),
+                                        _ptr(depths), _ptr(colors), _ptr(bin_ws), _ptr(ws), ws_bytes,
+                                        _ptr(image), _ptr(contrib), _ptr(final_tau), _ptr(ranges), _ptr(gsid),
+                                        st), lib)
         # the workspaces are consumed by kernels already enqueued on `st`; the caching
         # allocator only reuses them for later work on the same stream
+        if P > 0:
+            _remember_records(gsid, ws, lib.gsb_splat_records_offset(N, H, W, P), (us, cinv2ds, alphas, colors))
     return [image, contrib, final_tau, ranges, gsid]
+
+
+# The forward leaves the packed, sorted record stream in its workspace; splatB can reuse it
+# instead of gathering the same records again, provided it is called with the very tensors the
+# forward saw, unmodified (checked through data_ptr + torch's in-place version counter).
+_RECORD_CACHE = []  # [(gsid_ptr, P, ws, offset, ((ptr, version), ...))], newest first, <= 2 entries
+
+
+def _input_key(inputs):
+    try:
+        return tuple((t.data_ptr(), t._version) for t in inputs)
+    except RuntimeError:  # inference tensors have no version counter: never cache
+        return None
+
+
+def _remember_records(gsid, ws, offset, inputs):
+    key = _input_key(inputs)
+    if key is None:
+        return
+    _RECORD_CACHE.insert(0, (gsid.data_ptr(), gsid.numel(), ws, offset, key))
+    del _RECORD_CACHE[2:]
+
+
+def _cached_records(gsid, inputs):
+    key = _input_key(inputs)
+    if key is None:
+        return None
+    for gptr, P, ws, offset, k in _RECORD_CACHE:
+        if gptr == gsid.data_ptr() and P == gsid.numel() and k == key:
+            return ws.data_ptr() + offset
+    return None
+
+
+def clear_record_cache():
+    """Drop the (at most two) forward workspaces kept alive for splatB's benefit."""
+    del _RECORD_CACHE[:]
 
 
 def splatB(height, width, us, cinv2ds, alphas, depths, colors, contrib, final_tau,
@@ -223,11 +262,13 @@ def splatB(height, width, us, cinv2ds, alphas, depths, colors, contrib, final_ta
     da = torch.empty((N, 1, 1), **o); dcol = torch.empty((N, 1, 3), **o)
     lib = _L()
     with torch.cuda.device(dev):
-        ws_bytes = lib.gsb_splat_backward_workspace_bytes(N, H, W, P)
+        recs = _cached_records(gsid, (us, cinv2ds, alphas, colors)) if P > 0 else None
+        # with cached records only the [N,9] moment rows are needed from the workspace
+        ws_bytes = lib.gsb_splat_backward_workspace_bytes(N, H, W, 0 if recs else P)
         ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
         _lib.check(lib.gsb_splat_backward(H, W, N, P, _ptr(us), _ptr(cinv2ds), _ptr(alphas), _ptr(colors),
                                           _ptr(contrib), _ptr(final_tau), _ptr(ranges), _ptr(gsid), _ptr(dl),
-                                          _ptr(ws), ws_bytes, _ptr(du), _ptr(dc), _ptr(da), _ptr(dcol),
+                                          recs, _ptr(ws), ws_bytes, _ptr(du), _ptr(dc), _ptr(da), _ptr(dcol),
                                           _stream()), lib)
     return [du, dc, da, dcol]
 

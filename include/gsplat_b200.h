@@ -100,20 +100,29 @@ int gsb_preprocess_backward(int N, int sh_dim3, const float *pws, const float *r
  * Replaces getRects + thrust::inclusive_scan + the D2H read of the total
  * (gausplat.cu:54-67, kernel.cu:82-122).  depths and areas are READ-WRITE (Gaussians that
  * touch no tile get depths = -1, areas = 0).  Leaves rects/offsets in `bin_ws` for phase 2.
- * Writes the patch count to *P_host after synchronising `stream` (the one host sync). */
+ * Writes the patch count to *P_host and the largest depth key (uint32)(depth*1000) of a
+ * binned Gaussian to *depth_key_max_host (nullable) after synchronising `stream` (the one
+ * host sync; the reference has the same read-back, gausplat.cu:67). */
 size_t gsb_splat_bin_workspace_bytes(int N);
 int gsb_splat_bin(int H, int W, int N, const float *us, float *depths, int32_t *areas,
-                  void *bin_ws, size_t bin_ws_bytes, int64_t *P_host, gsb_stream_t stream);
+                  void *bin_ws, size_t bin_ws_bytes, int64_t *P_host, uint32_t *depth_key_max_host,
+                  gsb_stream_t stream);
 
 /* ---- splat, phase 2: keys, duplicate-key radix sort, tile ranges, record packing, draw.
  * Replaces createKeys + thrust::sort_by_key + getRanges + draw (gausplat.cu:69-105,
  * kernel.cu:46-80,125-271).  `alphas` is [N] (or [N,1]).  Outputs: image[3,H,W] planar,
  * contrib[H,W] int32, final_tau[H,W], patch_range_per_tile[T,2] int32 (T = tiles),
  * gsid_per_patch[P] int32 (Gaussian id of every patch in (tile, depth-mm, id) order).
- * Every output element is written (no pre-zeroing needed). */
+ * Every output element is written (no pre-zeroing needed).
+ * depth_key_max: the value phase 1 returned (bounds the sort width; keys are packed into 32
+ * bits when tile and depth bits fit), or 0xFFFFFFFF for the reference's full 64-bit layout --
+ * the resulting order is the same.  After the call the packed 48-B record stream of the P
+ * patches sits at ws + gsb_splat_records_offset(...) and may be handed to
+ * gsb_splat_backward as `packed_records` while `ws` and the inputs are unchanged. */
 size_t gsb_splat_workspace_bytes(int N, int H, int W, int64_t P);
-int gsb_splat_render(int H, int W, int N, int64_t P, const float *us, const float *cinv2ds,
-                     const float *alphas, const float *depths, const float *colors,
+size_t gsb_splat_records_offset(int N, int H, int W, int64_t P);
+int gsb_splat_render(int H, int W, int N, int64_t P, uint32_t depth_key_max, const float *us,
+                     const float *cinv2ds, const float *alphas, const float *depths, const float *colors,
                      const void *bin_ws, void *ws, size_t ws_bytes, float *image,
                      int32_t *contrib, float *final_tau, int32_t *patch_range_per_tile,
                      int32_t *gsid_per_patch, gsb_stream_t stream);
@@ -121,12 +130,14 @@ int gsb_splat_render(int H, int W, int N, int64_t P, const float *us, const floa
 /* ---- splatB.  Replaces `splatB` (ext.cpp:20-32, gausplat.cu:114-159, kernel.cu:809-950).
  * Consumes the forward's contrib / final_tau / patch_range_per_tile / gsid_per_patch.
  * -> dloss_dus[N,1,2], dloss_dcinv2ds[N,1,3], dloss_dalphas[N,1,1], dloss_dcolors[N,1,3]
- * (zeroed inside). */
+ * (every element written).  packed_records: NULL (records are re-packed from
+ * gsid_per_patch and the four attribute arrays) or the forward's record stream. */
 size_t gsb_splat_backward_workspace_bytes(int N, int H, int W, int64_t P);
 int gsb_splat_backward(int H, int W, int N, int64_t P, const float *us, const float *cinv2ds,
                        const float *alphas, const float *colors, const int32_t *contrib,
                        const float *final_tau, const int32_t *patch_range_per_tile,
-                       const int32_t *gsid_per_patch, const float *dloss_dgammas, void *ws,
+                       const int32_t *gsid_per_patch, const float *dloss_dgammas,
+                       const void *packed_records, void *ws,
                        size_t ws_bytes, float *dloss_dus, float *dloss_dcinv2ds,
                        float *dloss_dalphas, float *dloss_dcolors, gsb_stream_t stream);
 

@@ -133,3 +133,48 @@ def test_preprocess_backward_vs_oracle_chain():
     for got, name in ((gpw, "pws"), (gsh, "shs"), (gs, "scales"), (gq, "rots")):
         e = np.abs(n(got).astype(np.float64) - ref[name]).max() / np.abs(ref[name]).max()
         assert e < 2e-5, (name, e)
+
+
+def test_record_cache_and_key_widths():
+    """splatB reuses the forward's packed records only for untouched inputs; 32- and 64-bit key
+    layouts (gsb_splat_render depth_key_max) give the same patch order."""
+    import ctypes as C
+    import gsplatcu as g
+    from easygaussiansplatting_b200 import _lib, ops
+    W, H, N = 320, 240, 20000
+    sc = scene(N, W, H, 3, 21)
+    us, ci, col, d, ar = ops.preprocess(t(sc["pws"]), t(sc["rots"]), t(sc["scales"]), t(sc["shs"]), t(sc["Rcw"]),
+                                        t(sc["tcw"]), t(sc["twc"]), sc["fx"], sc["fy"], sc["cx"], sc["cy"], W, H)
+    al = t(sc["alphas"])
+    dl = t(upstream_gradient(W, H, 1) * (3.0 * W * H))
+    out = g.splat(H, W, us, ci, al, d, col, ar)
+    assert ops._cached_records(out[4], (us, ci, al, col)) is not None
+    g1 = g.splatB(H, W, us, ci, al, d, col, out[1], out[2], out[3], out[4], dl)      # cached records
+    ops.clear_record_cache()
+    g2 = g.splatB(H, W, us, ci, al, d, col, out[1], out[2], out[3], out[4], dl)      # re-packed
+    for a, b in zip(g1, g2):
+        assert torch.allclose(a, b, rtol=1e-4, atol=1e-6 * a.abs().max().item())
+    # an in-place edit of an input invalidates the cache entry
+    out = g.splat(H, W, us, ci, al, d, col, ar)
+    col.mul_(1.0)
+    assert ops._cached_records(out[4], (us, ci, al, col)) is None
+    # 64-bit reference key layout through the C ABI == the packed 32-bit layout
+    lib = _lib.load()
+    st = torch.cuda.current_stream().cuda_stream
+    d2, ar2 = d.clone(), ar.clone()
+    bin_bytes = lib.gsb_splat_bin_workspace_bytes(N)
+    bin_ws = torch.empty(bin_bytes, dtype=torch.uint8, device=DEV)
+    P, dk = C.c_int64(0), C.c_uint32(0)
+    _lib.check(lib.gsb_splat_bin(H, W, N, us.data_ptr(), d2.data_ptr(), ar2.data_ptr(), bin_ws.data_ptr(), bin_bytes,
+                                 C.byref(P), C.byref(dk), st), lib)
+    P = int(P.value)
+    assert P == out[4].numel() and 200 <= dk.value <= 12000
+    ws_bytes = lib.gsb_splat_workspace_bytes(N, H, W, P)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=DEV)
+    img = torch.empty_like(out[0]); con = torch.empty_like(out[1]); ft = torch.empty_like(out[2])
+    rg = torch.empty_like(out[3]); gs = torch.empty_like(out[4])
+    _lib.check(lib.gsb_splat_render(H, W, N, P, 0xFFFFFFFF, us.data_ptr(), ci.data_ptr(), al.data_ptr(),
+                                    d2.data_ptr(), col.data_ptr(), bin_ws.data_ptr(), ws.data_ptr(), ws_bytes,
+                                    img.data_ptr(), con.data_ptr(), ft.data_ptr(), rg.data_ptr(), gs.data_ptr(), st),
+               lib)
+    assert torch.equal(gs, out[4]) and torch.equal(rg, out[3]) and torch.equal(img, out[0])
