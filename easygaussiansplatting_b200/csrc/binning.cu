@@ -59,8 +59,17 @@ __global__ void __launch_bounds__(256) k_rects(int N, const float2 *__restrict__
     rects[i] = rect;
     counts[i] = n;
   }
+  // one atomicMax per CTA (a per-warp atomic on a single address serialises 31k warps)
+  __shared__ uint32_t s_max[8];
   const uint32_t wmax = __reduce_max_sync(0xffffffffu, dk);
-  if ((threadIdx.x & 31) == 0 && wmax > 0) atomicMax(max_key, wmax);
+  if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = wmax;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t m = 0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) m = max(m, s_max[w]);
+    if (m > 0) atomicMax(max_key, m);
+  }
 }
 
 __global__ void k_total(int N, const uint32_t *__restrict__ incl, uint32_t *__restrict__ total) {
@@ -102,8 +111,8 @@ __global__ void __launch_bounds__(256) k_ranges(int64_t P, const KeyT *__restric
 
 // Gathers the four per-Gaussian attribute arrays (all L2 resident: 36 B/Gaussian) into the
 // sorted 48-B record stream the rasterizer streams with cp.async.bulk.
-// hx, hy: conservative half-extents of the region where alpha' can reach 0.002, i.e.
-// maha <= 2 ln(alpha / 0.002); computed in fp64 so the determinant does not cancel.
+// thr: the per-record bound of the warp-level culling test (common.cuh rec_can_touch); the
+// positive-definiteness check is done in fp64 so the determinant does not cancel.
 __global__ void __launch_bounds__(256) k_pack(int64_t P, const int32_t *__restrict__ gsid,
                                               const float2 *__restrict__ us,
                                               const float *__restrict__ cinv2ds,
@@ -116,23 +125,19 @@ __global__ void __launch_bounds__(256) k_pack(int64_t P, const int32_t *__restri
   const float A = __ldg(cinv2ds + 3 * (size_t)g), B = __ldg(cinv2ds + 3 * (size_t)g + 1),
               C = __ldg(cinv2ds + 3 * (size_t)g + 2);
   const float al = __ldg(alphas + g);
-  float hx = INFINITY, hy = INFINITY;
+  // thr = log2(alpha / 0.002): -log2(g) <= thr is necessary for alpha' >= 0.002 (rec_can_touch).
+  float thr = INFINITY;  // never cull unless the conic is a proper positive definite form
   if (al < ALPHA_SKIP) {
-    hx = hy = -INFINITY;  // alpha * g < 0.002 everywhere: never contributes
+    thr = -INFINITY;  // alpha * g < 0.002 everywhere: never contributes
   } else {
     const double det = (double)A * (double)C - (double)B * (double)B;
-    const double L = 2.0 * log((double)al / 0.002);
-    if (det > 0.0 && A > 0.f && C > 0.f && isfinite(det) && isfinite(L)) {
-      const double ex = sqrt(L * (double)C / det) * 1.00001 + 1e-3;
-      const double ey = sqrt(L * (double)A / det) * 1.00001 + 1e-3;
-      if (isfinite(ex) && isfinite(ey)) {
-        hx = __double2float_ru(ex);
-        hy = __double2float_ru(ey);
-      }
+    if (det > 0.0 && A > 0.f && C > 0.f && isfinite(det)) {
+      const float t = __double2float_ru(log2((double)al / 0.002) + 1e-5);
+      if (isfinite(t)) thr = t;
     }
   }
   Rec r;
-  r.q0 = make_float4(u.x, u.y, hx, hy);
+  r.q0 = make_float4(u.x, u.y, thr, 0.f);
   r.q1 = make_float4(-0.5f * LOG2E * A, -LOG2E * B, -0.5f * LOG2E * C, al);
   r.q2 = make_float4(__ldg(colors + 3 * (size_t)g), __ldg(colors + 3 * (size_t)g + 1),
                      __ldg(colors + 3 * (size_t)g + 2), __int_as_float(g));

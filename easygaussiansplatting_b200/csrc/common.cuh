@@ -16,7 +16,9 @@ constexpr float LOG2E = 1.4426950408889634f;
 
 // Packed per-patch record, 48 B, written by pack_records (binning.cu) in sorted order so a
 // tile's records are one contiguous 16-B aligned span -> one cp.async.bulk per batch.
-//   q0 = (ux, uy, hx, hy)      mean in pixels; conservative half-extents of {alpha' >= 0.002}
+//   q0 = (ux, uy, thr, 0)      mean in pixels; thr = log2(alpha / 0.002) (+margin): a pixel can
+//                              reach alpha' >= 0.002 only where -log2(g) <= thr
+//                              (+inf: never cull, -inf: never contributes)
 //   q1 = (a, b, c, alpha)      log2(g) = a dx^2 + b dx dy + c dy^2  (conic pre-scaled by
 //                              -0.5*log2e, -log2e, -0.5*log2e), opacity
 //   q2 = (r, g, b, gsid bits)
@@ -41,6 +43,35 @@ __device__ __forceinline__ float alpha_prime(const float4 &q1, float dx, float d
   float gg = ex2_approx(p);
   *g = gg;
   return fminf(ALPHA_CLAMP, q1.w * gg);
+}
+
+// Can this record reach alpha' >= 0.002 anywhere in the pixel rectangle [bx0,bx1] x [by0,by1]?
+// Exact minimum of the (positive definite) quadratic Q = -log2(g) over the continuous
+// rectangle: 0 if the mean lies inside, otherwise the smallest of the four edge minima (each a
+// clamped 1-D parabola).  Conservative by construction (continuous rectangle >= pixel centres)
+// plus an fp32 error allowance proportional to the largest term magnitude, so a record is only
+// dropped when every pixel of the rectangle would take the reference's `continue`
+// (kernel.cu:246) -- image, contrib and final_tau are unaffected.
+__device__ __forceinline__ bool rec_can_touch(const float4 &q0, const float4 &q1, float bx0, float bx1,
+                                              float by0, float by1) {
+  const float A = -q1.x, B = -q1.y, C = -q1.z;
+  const float dxl = q0.x - bx1, dxh = q0.x - bx0, dyl = q0.y - by1, dyh = q0.y - by0;
+  const bool inside = (dxl <= 0.f) && (dxh >= 0.f) && (dyl <= 0.f) && (dyh >= 0.f);
+  const float kx = __fdividef(-0.5f * B, C), ky = __fdividef(-0.5f * B, A);
+  float qmin = 3.0e38f;
+#pragma unroll
+  for (int e = 0; e < 2; e++) {
+    const float ex = e ? dxh : dxl;
+    const float dy = fminf(fmaxf(kx * ex, dyl), dyh);
+    qmin = fminf(qmin, fmaf(fmaf(B, ex, C * dy), dy, A * ex * ex));
+    const float ey = e ? dyh : dyl;
+    const float dx = fminf(fmaxf(ky * ey, dxl), dxh);
+    qmin = fminf(qmin, fmaf(fmaf(B, ey, A * dx), dx, C * ey * ey));
+  }
+  if (inside) qmin = 0.f;
+  const float X = fmaxf(fabsf(dxl), fabsf(dxh)), Y = fmaxf(fabsf(dyl), fabsf(dyh));
+  const float S = fmaf(A * X, X, fmaf(fabsf(B) * X, Y, C * Y * Y));
+  return !(qmin > q0.z + fmaf(2.0e-6f, S, 1.0e-5f));  // NaN anywhere keeps the record
 }
 
 // ---- mbarrier + bulk async copy (global -> shared), single-CTA forms

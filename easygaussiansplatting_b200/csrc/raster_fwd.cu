@@ -75,10 +75,7 @@ __global__ void __launch_bounds__(256) k_draw(int W, int H, int gx, const int2 *
       for (int c0 = 0; c0 < nrec; c0 += 32) {
         const int j = c0 + lane;
         bool hit = false;
-        if (j < nrec) {
-          const float4 q0 = sbuf[s][j].q0;
-          hit = (q0.x + q0.z >= bx0) && (q0.x - q0.z <= bx1) && (q0.y + q0.w >= by0) && (q0.y - q0.w <= by1);
-        }
+        if (j < nrec) hit = rec_can_touch(sbuf[s][j].q0, sbuf[s][j].q1, bx0, bx1, by0, by1);
         unsigned mask = __ballot_sync(0xffffffffu, hit);
         while (mask) {
           const int k = __ffs(mask) - 1;
