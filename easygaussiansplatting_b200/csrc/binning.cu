@@ -130,10 +130,12 @@ __global__ void __launch_bounds__(256) k_pack(int64_t P, const int32_t *__restri
   if (al < ALPHA_SKIP) {
     thr = -INFINITY;  // alpha * g < 0.002 everywhere: never contributes
   } else {
-    const double det = (double)A * (double)C - (double)B * (double)B;
-    if (det > 0.0 && A > 0.f && C > 0.f && isfinite(det)) {
-      const float t = __double2float_ru(log2((double)al / 0.002) + 1e-5);
-      if (isfinite(t)) thr = t;
+    // positive definite with a safety factor against fp32 cancellation in A C - B^2
+    const float ac = A * C;
+    const float det = fmaf(A, C, -B * B);
+    if (A > 0.f && C > 0.f && det > 1e-4f * ac && ac < 3.0e38f) {
+      const float t = __log2f(al * 500.0f) + 1e-4f;  // log2(alpha / 0.002), lg2.approx error << margin
+      if (t < 3.0e38f) thr = t;
     }
   }
   Rec r;

@@ -146,20 +146,19 @@ __global__ void __launch_bounds__(256) k_draw_bwd(
           const bool active = (idx < cont) && (ap >= ALPHA_SKIP);
           if (!__any_sync(0xffffffffu, active)) continue;
           const float4 q2 = r->q2;
-          float v[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+          // inactive lanes contribute exact zeros through the two scale factors
+          float dl_dap = 0.f, wc = 0.f;
           if (active) {
-            tau = __fdividef(tau, 1.0f - ap);
+            tau = tau * rcp_approx(1.0f - ap);  // 1 - alpha' >= 0.01: no denormal handling needed
             const float dc = fmaf(dlr, q2.x, fmaf(dlg, q2.y, dlb * q2.z));
             const float diff = dc - sdot;
-            const float dl_dap = tau * diff;
+            dl_dap = tau * diff;
             sdot = fmaf(ap, diff, sdot);
-            const float w = dl_dap * ap;
-            const float wc = ap * tau;
-            const float wdx = w * dx, wdy = w * dy;
-            v[0] = wdx; v[1] = wdy; v[2] = wdx * dx; v[3] = wdx * dy; v[4] = wdy * dy;
-            v[5] = dl_dap * g;
-            v[6] = wc * dlr; v[7] = wc * dlg; v[8] = wc * dlb;
+            wc = ap * tau;
           }
+          const float w = dl_dap * ap;
+          const float wdx = w * dx, wdy = w * dy;
+          const float v[9] = {wdx, wdy, wdx * dx, wdx * dy, wdy * dy, dl_dap * g, wc * dlr, wc * dlg, wc * dlb};
           const float tot = split_reduce9(v, lane);
           if (slot >= 0) atomicAdd(mom_lane + (size_t)__float_as_int(q2.w) * MOM, tot);
         }

@@ -61,10 +61,10 @@ __global__ void __launch_bounds__(256) k_draw(int W, int H, int gx, const int2 *
 
   const float fpx = (float)px, fpy = (float)py;
   const float bx0 = (float)rx0, bx1 = (float)(rx0 + 7), by0 = (float)ry0, by1 = (float)(ry0 + 3);
-  float tau = 1.0f, cr = 0.f, cg = 0.f, cb = 0.f;
+  // a pixel is finished exactly when tau < 1e-4; pixels outside the image start finished
+  float tau = inside ? 1.0f : 0.0f, cr = 0.f, cg = 0.f, cb = 0.f;
   int cont = 0;
-  bool done = !inside;
-  bool warp_done = __all_sync(0xffffffffu, done);
+  bool warp_done = __all_sync(0xffffffffu, tau < TAU_STOP);
 
   int b = 0;
   for (; b < nb; b++) {
@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(256) k_draw(int W, int H, int gx, const int2 *
           const float4 q0 = r->q0, q1 = r->q1;
           float g;
           const float ap = alpha_prime(q1, q0.x - fpx, q0.y - fpy, &g);
-          if (!done && ap >= ALPHA_SKIP) {
+          if (tau >= TAU_STOP && ap >= ALPHA_SKIP) {
             const float4 q2 = r->q2;
             const float w = tau * ap;
             cr = fmaf(w, q2.x, cr);
@@ -92,10 +92,9 @@ __global__ void __launch_bounds__(256) k_draw(int W, int H, int gx, const int2 *
             cb = fmaf(w, q2.z, cb);
             cont = b * DRAW_BATCH + c0 + k + 1;
             tau = tau * (1.0f - ap);
-            done = tau < TAU_STOP;
           }
         }
-        warp_done = __all_sync(0xffffffffu, done);
+        warp_done = __all_sync(0xffffffffu, tau < TAU_STOP);
         if (warp_done) break;
       }
     }
