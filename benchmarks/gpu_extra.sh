@@ -1,0 +1,13 @@
+#!/usr/bin/env bash
+# extras: config-4 sweep, training stand-in, reference comparison
+set -x
+mkdir -p gpurun_out
+python -c "import __graft_entry__ as g; g.build()" 2>&1 | tail -2
+for what in "$@"; do
+  case $what in
+    sweep) timeout 1500 python benchmarks/sweep_config4.py --iters 8 > gpurun_out/sweep.log 2>&1; tail -12 gpurun_out/sweep.log | cut -c1-400 ;;
+    train) timeout 900 python benchmarks/train_synthetic.py --n 100000 --views 4 --iters 200 --size 640x360 > gpurun_out/train.log 2>&1; tail -14 gpurun_out/train.log ;;
+    traintest) timeout 900 python -m pytest tests/test_gpu_training.py -m gpu -x -q 2>&1 | tail -5 ;;
+    mgpu) N=$(nvidia-smi -L | wc -l); timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 20 --warmup 5 > gpurun_out/bench_gpus$N.json 2> gpurun_out/bench_gpus$N.err; tail -5 gpurun_out/bench_gpus$N.err; cat gpurun_out/bench_gpus$N.json ;;
+  esac
+done
