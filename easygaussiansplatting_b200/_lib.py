@@ -28,6 +28,7 @@ SIGNATURES = {
     "gsb_splat_backward_workspace_bytes": (_sz, [_i, _i, _i, _i64]),
     "gsb_splat_backward": (_i, [_i, _i, _i, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                 _sz, _vp, _vp, _vp, _vp, _vp]),
+    "gsb_set_option": (_i, [C.c_char_p, _i]),
     "gsb_profile_enable": (None, [_i]),
     "gsb_profile_kernels": (_i, []),
     "gsb_profile_kernel_name": (C.c_char_p, [_i]),

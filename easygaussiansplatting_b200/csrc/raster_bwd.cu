@@ -222,7 +222,10 @@ int launch_draw_backward(int H, int W, int N, const int32_t *ranges, const Rec *
   const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
   if (gx <= 0 || gy <= 0 || N <= 0) return 0;
   GSB_CUDA_TRY(cudaMemsetAsync(moments, 0, sizeof(float) * MOM * (size_t)N, st));
-  if (recs != nullptr) {
+  if (recs != nullptr && raster_variant() == 2) {
+    int rc = launch_draw_bwd2_kernel(H, W, ranges, recs, contrib, final_tau, dloss_dgammas, moments, st);
+    if (rc) return rc;
+  } else if (recs != nullptr) {
     ProfScope ps(K_DRAW_BWD, st);
     k_draw_bwd<<<gx * gy, 256, 0, st>>>(W, H, gx, reinterpret_cast<const int2 *>(ranges), recs, contrib,
                                         final_tau, dloss_dgammas, moments);
