@@ -139,8 +139,7 @@ __global__ void __launch_bounds__(128) k_draw_bwd2(
           const float ap0 = fminf(ALPHA_CLAMP, ag.x), ap1 = fminf(ALPHA_CLAMP, ag.y);
           const bool a0 = (idx < cont0) && (ap0 >= ALPHA_SKIP);
           const bool a1 = (idx < cont1) && (ap1 >= ALPHA_SKIP);
-          const unsigned amask = __ballot_sync(0xffffffffu, a0 || a1);
-          if (amask == 0u) continue;
+          if (!__any_sync(0xffffffffu, a0 || a1)) continue;
           const float4 q2 = r->q2;
           // an inactive pixel replays alpha' = 0: tau / (1 - 0) = tau, all nine terms exactly 0
           const float2 e = g2(a0 ? ap0 : 0.0f, a1 ? ap1 : 0.0f);
@@ -158,18 +157,8 @@ __global__ void __launch_bounds__(128) k_draw_bwd2(
           const float2 m6 = __fmul2_rn(wc, dlr), m7 = __fmul2_rn(wc, dlg), m8 = __fmul2_rn(wc, dlb);
           const float v[9] = {wdx.x + wdx.y, wdy.x + wdy.y, m2.x + m2.y, m3.x + m3.y, m4.x + m4.y,
                               m5.x + m5.y, m6.x + m6.y, m7.x + m7.y, m8.x + m8.y};
-          if (__popc(amask) <= 2) {
-            // fringe overlap (one or two lanes): nine direct REDs cost fewer issue slots than the
-            // 12-shuffle reduction
-            if (a0 || a1) {
-              float *row = moments + (size_t)__float_as_int(q2.w) * MOM2;
-#pragma unroll
-              for (int i = 0; i < MOM2; i++) atomicAdd(row + i, v[i]);
-            }
-          } else {
-            const float tot = split_reduce9_v2(v, lane);
-            if (slot >= 0) atomicAdd(mom_lane + (size_t)__float_as_int(q2.w) * MOM2, tot);
-          }
+          const float tot = split_reduce9_v2(v, lane);
+          if (slot >= 0) atomicAdd(mom_lane + (size_t)__float_as_int(q2.w) * MOM2, tot);
         }
       }
     }
