@@ -156,6 +156,8 @@ def run_ours(args, rank, world):
     from easygaussiansplatting_b200.parallel import allreduce_grads
     from easygaussiansplatting_b200.scene import ring_camera, synthetic_scene, upstream_gradient
 
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line
     local = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -265,6 +267,14 @@ def run_ours(args, rank, world):
     value = pix * args.steps / (ms_dev * 1e-3) / 1e6
     e2e = pix * args.steps / (ms_e2e * 1e-3) / 1e6
 
+    allreduce = None
+    if world > 1:  # the gradient exchange alone (bytes, device time, max over ranks)
+        nbytes = 0
+        ms_ar = timed(lambda: allreduce_grads([p.grad for p in leaves]), 10, 3)
+        nbytes = allreduce_grads([p.grad for p in leaves])
+        allreduce = {"bytes": int(nbytes), "ms": ms_ar / 10,
+                     "algbw_GBps": nbytes / (ms_ar / 10 * 1e-3) / 1e9}
+
     # ---- per-kernel durations with CUDA events on the launch stream (roofline leg)
     prof_steps = 5
     lib.gsb_profile_enable(1)
@@ -340,6 +350,8 @@ def run_ours(args, rank, world):
         "gpu_launches": int(launches),
         "clocks": clocks,
     }
+    if allreduce is not None:
+        line["allreduce"] = allreduce
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

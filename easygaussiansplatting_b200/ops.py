@@ -321,8 +321,15 @@ def preprocessB(pws, rots, scales, shs, Rcw, tcw, twc, focal_x, focal_y, center_
         raise ValueError("shs must be [N, 3k] with k in {1,4,9,16}, got %s" % (tuple(shs.shape),))
     k = shs.shape[1] // 3
     o = dict(dtype=torch.float32, device=pws.device)
-    gpw = torch.empty((N, 3), **o); gsh = torch.empty((N, 3 * k), **o)
-    gs = torch.empty((N, 3), **o); gq = torch.empty((N, 4), **o)
+    # one flat bucket [dshs | drots | dpws | dscales]: a multi-GPU caller can all-reduce the four
+    # gradients in place with a single collective (parallel.allreduce_grads); every view starts
+    # 16-byte aligned (3k*N and 4*N floats are multiples of 4 elements when N % 4 == 0; the
+    # kernels fall back to scalar stores otherwise)
+    bucket = torch.empty((N * (3 * k + 10),), **o)
+    gsh = bucket[:N * 3 * k].view(N, 3 * k)
+    gq = bucket[N * 3 * k:N * (3 * k + 4)].view(N, 4)
+    gpw = bucket[N * (3 * k + 4):N * (3 * k + 7)].view(N, 3)
+    gs = bucket[N * (3 * k + 7):].view(N, 3)
     lib = _L()
     with torch.cuda.device(pws.device):
         _lib.check(lib.gsb_preprocess_backward(

@@ -82,6 +82,15 @@ for i, t in enumerate([grads[0], grads[1], grads[3]]):
     s = sum(w[i] for w in want)
     assert torch.allclose(t, s, atol=1e-6), (rank, i)
 assert [view_index(3, r, world) for r in range(world)] == [3 * world + r for r in range(world)]
+# gradients that are views tiling one flat bucket (what ops.preprocessB returns) are reduced in place
+bucket = torch.arange(50 * 10, dtype=torch.float32) * (rank + 1)
+views = [bucket[:200].view(50, 4), bucket[200:350].view(50, 3), bucket[350:].view(50, 3)]
+extra = torch.full((50, 1), float(rank + 1))
+nb = allreduce_grads(views + [extra])
+assert nb == 4 * (500 + 50)
+tot = sum(range(1, world + 1))
+assert torch.equal(bucket, torch.arange(500, dtype=torch.float32) * tot) and torch.all(extra == tot)
+assert views[1].data_ptr() == bucket.data_ptr() + 800
 dist.barrier(); dist.destroy_process_group()
 print("ok", rank)
 """
