@@ -156,8 +156,8 @@ def run_ours(args, rank, world):
     from easygaussiansplatting_b200.parallel import allreduce_grads
     from easygaussiansplatting_b200.scene import ring_camera, synthetic_scene, upstream_gradient
 
-    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-        os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line
+    # NCCL writes its version banner / diagnostics to stdout; keep stdout to the one JSON line
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     local = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
