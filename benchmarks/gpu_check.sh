@@ -22,8 +22,14 @@ for what in "$@"; do
           python benchmarks/profile_step.py 2 fused > gpurun_out/ncu_full.log 2>&1
       tail -3 gpurun_out/ncu_full.log ;;
     sanitize)
-      timeout 900 compute-sanitizer --tool memcheck python -m pytest tests/test_gpu_parity.py -m gpu -x -q \
-          -k "not config2 and not 50000" 2>&1 | tail -15 ;;
+      timeout 900 compute-sanitizer --tool memcheck python -m pytest tests/test_gpu_parity.py tests/test_gpu_fused.py \
+          -m gpu -x -q -k "not config2 and not 50000 and not 100000" > gpurun_out/sanitize_memcheck.log 2>&1
+      grep -E "=========" gpurun_out/sanitize_memcheck.log | grep -v "Host Frame" | head -30
+      tail -3 gpurun_out/sanitize_memcheck.log
+      timeout 900 compute-sanitizer --tool racecheck python -m pytest tests/test_gpu_parity.py -m gpu -x -q \
+          -k "splat_and_splatB_vs_oracle and 200" > gpurun_out/sanitize_racecheck.log 2>&1
+      grep -E "=========" gpurun_out/sanitize_racecheck.log | grep -v "Host Frame" | head -20
+      tail -3 gpurun_out/sanitize_racecheck.log ;;
   esac
 done
 ls -la gpurun_out
