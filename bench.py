@@ -416,6 +416,12 @@ def main():
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
+    # stdout carries exactly one JSON line: native libraries (NCCL's version banner) write to
+    # fd 1 directly, so fd 1 is pointed at stderr and the line goes to a private copy of stdout
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = real_stdout
     if args.impl == "reference":
         run_reference(args, rank)
     else:
