@@ -30,6 +30,14 @@ def scene(N, W, H, sh_dim, seed):
     sc["pws"][idx, 2] = rng.uniform(-1.0, 0.19, len(idx)).astype(np.float32)
     wide = rng.choice(N, size=max(1, N // 50), replace=False)
     sc["pws"][wide, 0] *= 6.0
+    if seed % 2 == 1:  # a general camera pose, so Rcw / tcw / twc really take part
+        a, b = 0.15, -0.08
+        Ry = np.array([[np.cos(a), 0, np.sin(a)], [0, 1, 0], [-np.sin(a), 0, np.cos(a)]])
+        Rx = np.array([[1, 0, 0], [0, np.cos(b), -np.sin(b)], [0, np.sin(b), np.cos(b)]])
+        sc["Rcw"] = (Ry @ Rx).astype(np.float32)
+        sc["tcw"] = np.array([0.3, -0.2, 0.4], np.float32)
+        sc["twc"] = (-(sc["Rcw"].astype(np.float64).T @ sc["tcw"].astype(np.float64))).astype(np.float32)
+        sc["rots"] = (sc["rots"] * rng.uniform(0.8, 1.25, (N, 1))).astype(np.float32)  # un-normalised q
     return sc
 
 
@@ -74,7 +82,7 @@ def run_both(sc, W, H, seed=0):
 
 @pytest.mark.parametrize("N,W,H,sh_dim", [(20000, 320, 240, 48), (3000, 250, 130, 12), (500, 64, 64, 3)])
 def test_fused_function_matches_op_surface(N, W, H, sh_dim):
-    a, b = run_both(scene(N, W, H, sh_dim, N), W, H, N)
+    a, b = run_both(scene(N, W, H, sh_dim, N + (N // 1000) % 2), W, H, N)  # 3000 -> rotated camera
     assert torch.equal(a["mask"], b["mask"])
     # a radius that flips by one between the two fp32 evaluation orders changes a tile list
     # but not the picture beyond the alpha' < 0.002 tail

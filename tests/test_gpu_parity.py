@@ -75,6 +75,14 @@ def scene_with_culls(N, W, H, sh_dim, seed):
     sc["pws"][idx, 2] = rng.uniform(-1.0, 0.19, len(idx)).astype(np.float32)  # behind / too close
     wide = rng.choice(N, size=max(1, N // 50), replace=False)
     sc["pws"][wide, 0] *= 6.0  # outside the 1.3*tan_fov cone -> clamp active
+    if seed % 2 == 1:  # a general camera pose and un-normalised quaternions
+        a, b = 0.15, -0.08
+        Ry = np.array([[np.cos(a), 0, np.sin(a)], [0, 1, 0], [-np.sin(a), 0, np.cos(a)]])
+        Rx = np.array([[1, 0, 0], [0, np.cos(b), -np.sin(b)], [0, np.sin(b), np.cos(b)]])
+        sc["Rcw"] = (Ry @ Rx).astype(np.float32)
+        sc["tcw"] = np.array([0.3, -0.2, 0.4], np.float32)
+        sc["twc"] = (-(sc["Rcw"].astype(np.float64).T @ sc["tcw"].astype(np.float64))).astype(np.float32)
+        sc["rots"] = (sc["rots"] * rng.uniform(0.8, 1.25, (N, 1))).astype(np.float32)
     return sc
 
 
@@ -87,7 +95,8 @@ def test_stages_vs_oracle(N, sh_dim):
     us, pcs, depths, J = orc.project(sc["pws"], sc["Rcw"], sc["tcw"], sc["fx"], sc["fy"], sc["cx"], sc["cy"])
     d_gpu = n(o["depths"])
     culled = depths < 0
-    amb = np.abs(sc["pws"][:, 2] - 0.2) < 1e-5
+    z64 = sc["pws"].astype(np.float64) @ sc["Rcw"].astype(np.float64)[2] + float(sc["tcw"][2])
+    amb = np.abs(z64 - 0.2) < 1e-5
     assert np.array_equal((d_gpu < 0)[~amb], culled[~amb])
     check_vals(o["us"], us, "us"); check_vals(o["pcs"], pcs, "pcs"); check_vals(o["du_dpcs"], J, "du_dpcs")
     check_vals(o["depths"], depths, "depths")
@@ -209,6 +218,7 @@ def run_splat_case(N, W, H, sh_dim=3, seed=0, check_bwd=True, sc=None):
 @pytest.mark.parametrize("N,W,H", [(10000, 256, 256),      # BASELINE config 1 shape
                                    (3000, 250, 130),       # ragged right / bottom tiles
                                    (50000, 512, 512),      # config 4 corner
+                                   (4001, 320, 200),       # rotated camera, un-normalised quaternions
                                    (200, 64, 48)])
 def test_splat_and_splatB_vs_oracle(N, W, H):
     run_splat_case(N, W, H, seed=N)
