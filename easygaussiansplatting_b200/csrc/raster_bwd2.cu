@@ -44,7 +44,7 @@ __device__ __forceinline__ int slot_of_lane_v2(int lane) {
   return g < MOM2 ? g : -1;
 }
 
-__global__ void __launch_bounds__(128) k_draw_bwd2(
+__global__ void __launch_bounds__(128, 12) k_draw_bwd2(
     int W, int H, int gx, const int2 *__restrict__ ranges, const Rec *__restrict__ recs,
     const int32_t *__restrict__ contrib, const float *__restrict__ final_tau,
     const float *__restrict__ dloss_dgammas, float *__restrict__ moments) {
