@@ -249,13 +249,19 @@ int gsb_splat_render(int H, int W, int N, int64_t P, uint32_t depth_key_max, con
                                 patch_range_per_tile, gsid_per_patch, st);
   if (rc) return rc;
   const Rec *recs = P > 0 ? reinterpret_cast<const Rec *>(static_cast<char *>(ws) + SL.recs) : nullptr;
-  return launch_draw(H, W, patch_range_per_tile, recs, image, contrib, final_tau, st);
+  // with P == 0 the workspace may be a dummy: every tile is empty, any variant just writes zeros
+  int *tile_counter = P > 0 ? reinterpret_cast<int *>(static_cast<char *>(ws) + SL.counters) : nullptr;
+  if (tile_counter == nullptr) {
+    GSB_REQUIRE(ws != nullptr && ws_bytes >= sizeof(int), "splat: workspace too small");
+    tile_counter = static_cast<int *>(ws);
+  }
+  return launch_draw(H, W, patch_range_per_tile, recs, image, contrib, final_tau, tile_counter, st);
 }
 
 size_t gsb_splat_backward_workspace_bytes(int N, int H, int W, int64_t P) {
   (void)H; (void)W;
   // packed records (256-B aligned) + the [N,9] moment accumulators
-  return (size_t)(P > 0 ? P : 1) * sizeof(Rec) + 512 + (size_t)(N > 0 ? N : 1) * 9 * sizeof(float) + 256;
+  return (size_t)(P > 0 ? P : 1) * sizeof(Rec) + 512 + (size_t)(N > 0 ? N : 1) * 9 * sizeof(float) + 512;
 }
 
 int gsb_splat_backward(int H, int W, int N, int64_t P, const float *us, const float *cinv2ds,
@@ -277,6 +283,7 @@ int gsb_splat_backward(int H, int W, int N, int64_t P, const float *us, const fl
   Rec *recs = reinterpret_cast<Rec *>(base);
   uintptr_t mbase = (base + (size_t)(P_ws > 0 ? P_ws : 1) * sizeof(Rec) + 255) & ~(uintptr_t)255;
   float *moments = reinterpret_cast<float *>(mbase);
+  int *tile_counter = reinterpret_cast<int *>((mbase + (size_t)N * 9 * sizeof(float) + 255) & ~(uintptr_t)255);
   if (P > 0) {
     GSB_REQUIRE(us && alphas && colors && contrib && final_tau && patch_range_per_tile && gsid_per_patch &&
                     dloss_dgammas,
@@ -291,8 +298,8 @@ int gsb_splat_backward(int H, int W, int N, int64_t P, const float *us, const fl
   }
   // P == 0: nothing was drawn; the zeroed moment rows finalise to all-zero gradients
   return launch_draw_backward(H, W, N, patch_range_per_tile, P > 0 ? recs : nullptr, contrib, final_tau,
-                              dloss_dgammas, cinv2ds, moments, dloss_dus, dloss_dcinv2ds, dloss_dalphas,
-                              dloss_dcolors, st);
+                              dloss_dgammas, cinv2ds, moments, tile_counter, dloss_dus, dloss_dcinv2ds,
+                              dloss_dalphas, dloss_dcolors, st);
 }
 
 }  // extern "C"

@@ -217,6 +217,7 @@ int sort_layout(int N, int H, int W, int64_t P, SortLayout *out) {
   L.keys_b = o; o = align_up(o + n * sizeof(uint64_t), 256);
   L.vals_a = o; o = align_up(o + n * sizeof(int32_t), 256);
   L.recs = o;   o = align_up(o + n * sizeof(Rec), 256);
+  L.counters = o; o = align_up(o + 64, 256);  // persistent-kernel tile counter
   size_t tmp64 = 0, tmp32 = 0;
   const KeyPlan wide = key_plan(H, W, 0xffffffffu);
   cudaError_t e = cub::DeviceRadixSort::SortPairs(nullptr, tmp64, (uint64_t *)nullptr, (uint64_t *)nullptr,

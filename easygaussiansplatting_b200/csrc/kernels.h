@@ -56,7 +56,7 @@ int launch_bin(int H, int W, int N, const float *us, float *depths, int32_t *are
                const BinLayout &L, cudaStream_t st);
 
 struct SortLayout {  // carve-up of the phase-2 workspace
-  size_t keys_a, keys_b, vals_a, recs, sort_tmp, sort_tmp_bytes, bytes;
+  size_t keys_a, keys_b, vals_a, recs, counters, sort_tmp, sort_tmp_bytes, bytes;
 };
 int sort_layout(int N, int H, int W, int64_t P, SortLayout *out);
 int launch_sort_and_pack(int H, int W, int N, int64_t P, uint32_t depth_key_max, const float *us,
@@ -71,17 +71,17 @@ int launch_pack_only(int64_t P, const int32_t *gsid_per_patch, const float *us, 
 // Set with gsb_set_option("raster_variant", v) or GSB_RASTER_VARIANT in the environment.
 int raster_variant();
 int launch_draw2(int H, int W, const int32_t *ranges, const Rec *recs, float *image, int32_t *contrib,
-                 float *final_tau, cudaStream_t st);
+                 float *final_tau, int *tile_counter, cudaStream_t st);
 int launch_draw_bwd2_kernel(int H, int W, const int32_t *ranges, const Rec *recs, const int32_t *contrib,
                             const float *final_tau, const float *dloss_dgammas, float *moments,
-                            cudaStream_t st);
+                            int *tile_counter, cudaStream_t st);
 
 // ---- rasterizer (raster_fwd.cu / raster_bwd.cu)
 int launch_draw(int H, int W, const int32_t *ranges, const Rec *recs, float *image, int32_t *contrib,
-                float *final_tau, cudaStream_t st);
+                float *final_tau, int *tile_counter, cudaStream_t st);
 int launch_draw_backward(int H, int W, int N, const int32_t *ranges, const Rec *recs, const int32_t *contrib,
                          const float *final_tau, const float *dloss_dgammas, const float *cinv2ds,
-                         float *moments, float *dloss_dus, float *dloss_dcinv2ds, float *dloss_dalphas,
-                         float *dloss_dcolors, cudaStream_t st);
+                         float *moments, int *tile_counter, float *dloss_dus, float *dloss_dcinv2ds,
+                         float *dloss_dalphas, float *dloss_dcolors, cudaStream_t st);
 
 }  // namespace gsb

@@ -45,141 +45,154 @@ __device__ __forceinline__ int slot_of_lane_v2(int lane) {
 }
 
 __global__ void __launch_bounds__(128, 12) k_draw_bwd2(
-    int W, int H, int gx, const int2 *__restrict__ ranges, const Rec *__restrict__ recs,
+    int W, int H, int gx, int T, const int2 *__restrict__ ranges, const Rec *__restrict__ recs,
     const int32_t *__restrict__ contrib, const float *__restrict__ final_tau,
-    const float *__restrict__ dloss_dgammas, float *__restrict__ moments) {
+    const float *__restrict__ dloss_dgammas, float *__restrict__ moments, int *__restrict__ tile_counter) {
   __shared__ Rec sbuf[2][BWD2_BATCH];
   __shared__ __align__(8) uint64_t mbar[2];
   __shared__ int s_wmax[4];
+  __shared__ int s_tile[2];
 
-  const int tile = blockIdx.x;
-  const int tx = tile % gx, ty = tile / gx;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int rx0 = tx * TILE + (warp & 1) * 8, ry0 = ty * TILE + (warp >> 1) * 8;
-  const int px = rx0 + 2 * (lane & 3), py = ry0 + (lane >> 2);
-  const bool in0 = px < W && py < H, in1 = px + 1 < W && py < H;
   const size_t HW = (size_t)H * W;
-  const size_t pix = (size_t)py * W + px;
-
-  const int2 range = __ldg(ranges + tile);
-  const int len = range.y - range.x;
-  if (len <= 0) return;
-
-  int cont0 = 0, cont1 = 0;
-  float2 tau = g2s(0.f), dlr = g2s(0.f), dlg = g2s(0.f), dlb = g2s(0.f);
-  if (in0) {
-    cont0 = min(__ldg(contrib + pix), len);
-    tau.x = __ldg(final_tau + pix);
-    dlr.x = __ldg(dloss_dgammas + pix);
-    dlg.x = __ldg(dloss_dgammas + HW + pix);
-    dlb.x = __ldg(dloss_dgammas + 2 * HW + pix);
-  }
-  if (in1) {
-    cont1 = min(__ldg(contrib + pix + 1), len);
-    tau.y = __ldg(final_tau + pix + 1);
-    dlr.y = __ldg(dloss_dgammas + pix + 1);
-    dlg.y = __ldg(dloss_dgammas + HW + pix + 1);
-    dlb.y = __ldg(dloss_dgammas + 2 * HW + pix + 1);
-  }
-  int wmax = max(cont0, cont1);
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
-  if (lane == 0) s_wmax[warp] = wmax;
+  const int slot = slot_of_lane_v2(lane);
+  float *const mom_lane = moments + (slot >= 0 ? slot : 0);
   if (tid == 0) {
     mbar_init(&mbar[0], 1);
     mbar_init(&mbar[1], 1);
     fence_mbar_init();
   }
-  __syncthreads();
-  const int bmax = max(max(s_wmax[0], s_wmax[1]), max(s_wmax[2], s_wmax[3]));
-  if (bmax <= 0) return;
-  const int nbn = (bmax + BWD2_BATCH - 1) / BWD2_BATCH;
-  const Rec *src = recs + range.x;
-  if (tid == 0) {
-    for (int bi = 0; bi < 2 && bi < nbn; bi++) {
-      const int b = nbn - 1 - bi;
-      const uint32_t bytes = (uint32_t)min(BWD2_BATCH, len - b * BWD2_BATCH) * (uint32_t)sizeof(Rec);
-      mbar_expect_tx(&mbar[bi], bytes);
-      bulk_g2s(&sbuf[bi][0], src + (size_t)b * BWD2_BATCH, bytes, &mbar[bi]);
+  uint32_t ph0 = 0, ph1 = 0;  // completed phases of the two stages (block-uniform)
+
+  // persistent CTA: tiles are pulled from an atomic counter (see raster_fwd2.cu)
+  for (int it = 0;; it++) {
+    if (tid == 0) s_tile[it & 1] = atomicAdd(tile_counter, 1);
+    __syncthreads();
+    const int tile = s_tile[it & 1];
+    if (tile >= T) break;
+    const int2 range = __ldg(ranges + tile);
+    const int len = range.y - range.x;
+    if (len <= 0) continue;
+    const int tx = tile % gx, ty = tile / gx;
+    const int rx0 = tx * TILE + (warp & 1) * 8, ry0 = ty * TILE + (warp >> 1) * 8;
+    const int px = rx0 + 2 * (lane & 3), py = ry0 + (lane >> 2);
+    const bool in0 = px < W && py < H, in1 = px + 1 < W && py < H;
+    const size_t pix = (size_t)py * W + px;
+
+    int cont0 = 0, cont1 = 0;
+    float2 tau = g2s(0.f), dlr = g2s(0.f), dlg = g2s(0.f), dlb = g2s(0.f);
+    if (in0) {
+      cont0 = min(__ldg(contrib + pix), len);
+      tau.x = __ldg(final_tau + pix);
+      dlr.x = __ldg(dloss_dgammas + pix);
+      dlg.x = __ldg(dloss_dgammas + HW + pix);
+      dlb.x = __ldg(dloss_dgammas + 2 * HW + pix);
     }
-  }
-
-  const float2 npx = g2(-(float)px, -(float)(px + 1));
-  const float fpy = (float)py;
-  const float bx0 = (float)rx0, bx1 = (float)(rx0 + 7), by0 = (float)ry0, by1 = (float)(ry0 + 7);
-  const int slot = slot_of_lane_v2(lane);
-  float *const mom_lane = moments + (slot >= 0 ? slot : 0);
-  float2 sdot = g2s(0.f);  // dL/dgamma . gamma_next, per pixel
-
-  for (int bi = 0; bi < nbn; bi++) {
-    const int b = nbn - 1 - bi;
-    const int s = bi & 1;
-    mbar_wait(&mbar[s], (bi >> 1) & 1);
-    const int nrec = min(BWD2_BATCH, len - b * BWD2_BATCH);
-    if (b * BWD2_BATCH < wmax) {
-      for (int c0 = ((nrec - 1) >> 5) << 5; c0 >= 0; c0 -= 32) {
-        const int j = c0 + lane;
-        bool hit = false;
-        if (j < nrec && b * BWD2_BATCH + j < wmax)
-          hit = rec_can_touch(sbuf[s][j].q0, sbuf[s][j].q1, bx0, bx1, by0, by1);
-        unsigned mask = __ballot_sync(0xffffffffu, hit);
-        while (mask) {
-          const int k = 31 - __clz(mask);  // back to front
-          mask &= ~(1u << k);
-          const Rec *r = &sbuf[s][c0 + k];
-          const int idx = b * BWD2_BATCH + c0 + k;
-          const float4 q0 = r->q0, q1 = r->q1;
-          const float2 dx = __fadd2_rn(g2s(q0.x), npx);
-          const float dy = q0.y - fpy;
-          const float cdy2 = (q1.z * dy) * dy;
-          const float2 t = __ffma2_rn(g2s(q1.y), g2s(dy), __fmul2_rn(g2s(q1.x), dx));
-          const float2 p = __ffma2_rn(t, dx, g2s(cdy2));
-          const float2 gg = g2(ex2_approx(fminf(p.x, 0.0f)), ex2_approx(fminf(p.y, 0.0f)));
-          const float2 ag = __fmul2_rn(g2s(q1.w), gg);
-          const float ap0 = fminf(ALPHA_CLAMP, ag.x), ap1 = fminf(ALPHA_CLAMP, ag.y);
-          const bool a0 = (idx < cont0) && (ap0 >= ALPHA_SKIP);
-          const bool a1 = (idx < cont1) && (ap1 >= ALPHA_SKIP);
-          if (!__any_sync(0xffffffffu, a0 || a1)) continue;
-          const float4 q2 = r->q2;
-          // an inactive pixel replays alpha' = 0: tau / (1 - 0) = tau, all nine terms exactly 0
-          const float2 e = g2(a0 ? ap0 : 0.0f, a1 ? ap1 : 0.0f);
-          const float2 om = __fadd2_rn(g2s(1.0f), g2(-e.x, -e.y));
-          tau = __fmul2_rn(tau, g2(a0 ? rcp_approx(om.x) : 1.0f, a1 ? rcp_approx(om.y) : 1.0f));
-          const float2 dc = __ffma2_rn(dlr, g2s(q2.x), __ffma2_rn(dlg, g2s(q2.y), __fmul2_rn(dlb, g2s(q2.z))));
-          const float2 diff = __fadd2_rn(dc, g2(-sdot.x, -sdot.y));
-          sdot = __ffma2_rn(e, diff, sdot);
-          const float2 dl_dap = __fmul2_rn(g2(a0 ? tau.x : 0.0f, a1 ? tau.y : 0.0f), diff);
-          const float2 wc = __fmul2_rn(e, tau);
-          const float2 w = __fmul2_rn(dl_dap, e);
-          const float2 wdx = __fmul2_rn(w, dx), wdy = __fmul2_rn(w, g2s(dy));
-          const float2 m2 = __fmul2_rn(wdx, dx), m3 = __fmul2_rn(wdx, g2s(dy)), m4 = __fmul2_rn(wdy, g2s(dy));
-          const float2 m5 = __fmul2_rn(dl_dap, gg);
-          const float2 m6 = __fmul2_rn(wc, dlr), m7 = __fmul2_rn(wc, dlg), m8 = __fmul2_rn(wc, dlb);
-          const float v[9] = {wdx.x + wdx.y, wdy.x + wdy.y, m2.x + m2.y, m3.x + m3.y, m4.x + m4.y,
-                              m5.x + m5.y, m6.x + m6.y, m7.x + m7.y, m8.x + m8.y};
-          const float tot = split_reduce9_v2(v, lane);
-          if (slot >= 0) atomicAdd(mom_lane + (size_t)__float_as_int(q2.w) * MOM2, tot);
-        }
+    if (in1) {
+      cont1 = min(__ldg(contrib + pix + 1), len);
+      tau.y = __ldg(final_tau + pix + 1);
+      dlr.y = __ldg(dloss_dgammas + pix + 1);
+      dlg.y = __ldg(dloss_dgammas + HW + pix + 1);
+      dlb.y = __ldg(dloss_dgammas + 2 * HW + pix + 1);
+    }
+    int wmax = max(cont0, cont1);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
+    if (lane == 0) s_wmax[warp] = wmax;
+    __syncthreads();
+    const int bmax = max(max(s_wmax[0], s_wmax[1]), max(s_wmax[2], s_wmax[3]));
+    if (bmax <= 0) continue;
+    const int nbn = (bmax + BWD2_BATCH - 1) / BWD2_BATCH;  // batches [0, nbn) are needed
+    const Rec *src = recs + range.x;
+    if (tid == 0) {
+      for (int bi = 0; bi < 2 && bi < nbn; bi++) {
+        const int b = nbn - 1 - bi;
+        const uint32_t bytes = (uint32_t)min(BWD2_BATCH, len - b * BWD2_BATCH) * (uint32_t)sizeof(Rec);
+        fence_proxy_async();
+        mbar_expect_tx(&mbar[bi], bytes);
+        bulk_g2s(&sbuf[bi][0], src + (size_t)b * BWD2_BATCH, bytes, &mbar[bi]);
       }
     }
-    __syncthreads();  // every warp is done with stage s
-    if (tid == 0 && bi + 2 < nbn) {
-      const int b2 = nbn - 1 - (bi + 2);
-      const uint32_t bytes = (uint32_t)min(BWD2_BATCH, len - b2 * BWD2_BATCH) * (uint32_t)sizeof(Rec);
-      fence_proxy_async();
-      mbar_expect_tx(&mbar[s], bytes);
-      bulk_g2s(&sbuf[s][0], src + (size_t)b2 * BWD2_BATCH, bytes, &mbar[s]);
+
+    const float2 npx = g2(-(float)px, -(float)(px + 1));
+    const float fpy = (float)py;
+    const float bx0 = (float)rx0, bx1 = (float)(rx0 + 7), by0 = (float)ry0, by1 = (float)(ry0 + 7);
+    float2 sdot = g2s(0.f);  // dL/dgamma . gamma_next, per pixel
+
+    for (int bi = 0; bi < nbn; bi++) {
+      const int b = nbn - 1 - bi;
+      const int s = bi & 1;
+      if (s == 0) { mbar_wait(&mbar[0], ph0 & 1); ph0++; } else { mbar_wait(&mbar[1], ph1 & 1); ph1++; }
+      const int nrec = min(BWD2_BATCH, len - b * BWD2_BATCH);
+      if (b * BWD2_BATCH < wmax) {
+        for (int c0 = ((nrec - 1) >> 5) << 5; c0 >= 0; c0 -= 32) {
+          const int j = c0 + lane;
+          bool hit = false;
+          if (j < nrec && b * BWD2_BATCH + j < wmax)
+            hit = rec_can_touch(sbuf[s][j].q0, sbuf[s][j].q1, bx0, bx1, by0, by1);
+          unsigned mask = __ballot_sync(0xffffffffu, hit);
+          while (mask) {
+            const int k = 31 - __clz(mask);  // back to front
+            mask &= ~(1u << k);
+            const Rec *r = &sbuf[s][c0 + k];
+            const int idx = b * BWD2_BATCH + c0 + k;
+            const float4 q0 = r->q0, q1 = r->q1;
+            const float2 dx = __fadd2_rn(g2s(q0.x), npx);
+            const float dy = q0.y - fpy;
+            const float cdy2 = (q1.z * dy) * dy;
+            const float2 t = __ffma2_rn(g2s(q1.y), g2s(dy), __fmul2_rn(g2s(q1.x), dx));
+            const float2 p = __ffma2_rn(t, dx, g2s(cdy2));
+            const float2 gg = g2(ex2_approx(fminf(p.x, 0.0f)), ex2_approx(fminf(p.y, 0.0f)));
+            const float2 ag = __fmul2_rn(g2s(q1.w), gg);
+            const float ap0 = fminf(ALPHA_CLAMP, ag.x), ap1 = fminf(ALPHA_CLAMP, ag.y);
+            const bool a0 = (idx < cont0) && (ap0 >= ALPHA_SKIP);
+            const bool a1 = (idx < cont1) && (ap1 >= ALPHA_SKIP);
+            if (!__any_sync(0xffffffffu, a0 || a1)) continue;
+            const float4 q2 = r->q2;
+            // an inactive pixel replays alpha' = 0: tau / (1 - 0) = tau, all nine terms exactly 0
+            const float2 e = g2(a0 ? ap0 : 0.0f, a1 ? ap1 : 0.0f);
+            const float2 om = __fadd2_rn(g2s(1.0f), g2(-e.x, -e.y));
+            tau = __fmul2_rn(tau, g2(a0 ? rcp_approx(om.x) : 1.0f, a1 ? rcp_approx(om.y) : 1.0f));
+            const float2 dc = __ffma2_rn(dlr, g2s(q2.x), __ffma2_rn(dlg, g2s(q2.y), __fmul2_rn(dlb, g2s(q2.z))));
+            const float2 diff = __fadd2_rn(dc, g2(-sdot.x, -sdot.y));
+            sdot = __ffma2_rn(e, diff, sdot);
+            const float2 dl_dap = __fmul2_rn(g2(a0 ? tau.x : 0.0f, a1 ? tau.y : 0.0f), diff);
+            const float2 wc = __fmul2_rn(e, tau);
+            const float2 w = __fmul2_rn(dl_dap, e);
+            const float2 wdx = __fmul2_rn(w, dx), wdy = __fmul2_rn(w, g2s(dy));
+            const float2 m2 = __fmul2_rn(wdx, dx), m3 = __fmul2_rn(wdx, g2s(dy)), m4 = __fmul2_rn(wdy, g2s(dy));
+            const float2 m5 = __fmul2_rn(dl_dap, gg);
+            const float2 m6 = __fmul2_rn(wc, dlr), m7 = __fmul2_rn(wc, dlg), m8 = __fmul2_rn(wc, dlb);
+            const float v[9] = {wdx.x + wdx.y, wdy.x + wdy.y, m2.x + m2.y, m3.x + m3.y, m4.x + m4.y,
+                                m5.x + m5.y, m6.x + m6.y, m7.x + m7.y, m8.x + m8.y};
+            const float tot = split_reduce9_v2(v, lane);
+            if (slot >= 0) atomicAdd(mom_lane + (size_t)__float_as_int(q2.w) * MOM2, tot);
+          }
+        }
+      }
+      __syncthreads();  // every warp is done with stage s
+      if (tid == 0 && bi + 2 < nbn) {
+        const int b2 = nbn - 1 - (bi + 2);
+        const uint32_t bytes = (uint32_t)min(BWD2_BATCH, len - b2 * BWD2_BATCH) * (uint32_t)sizeof(Rec);
+        fence_proxy_async();
+        mbar_expect_tx(&mbar[s], bytes);
+        bulk_g2s(&sbuf[s][0], src + (size_t)b2 * BWD2_BATCH, bytes, &mbar[s]);
+      }
     }
   }
 }
 
+int persistent_grid(int T, int ctas_per_sm);  // raster_fwd2.cu
+
 int launch_draw_bwd2_kernel(int H, int W, const int32_t *ranges, const Rec *recs, const int32_t *contrib,
                             const float *final_tau, const float *dloss_dgammas, float *moments,
-                            cudaStream_t st) {
+                            int *tile_counter, cudaStream_t st) {
   const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
+  const int T = gx * gy;
+  GSB_CUDA_TRY(cudaMemsetAsync(tile_counter, 0, sizeof(int), st));
   ProfScope ps(K_DRAW_BWD, st);
-  k_draw_bwd2<<<gx * gy, 128, 0, st>>>(W, H, gx, reinterpret_cast<const int2 *>(ranges), recs, contrib, final_tau,
-                                       dloss_dgammas, moments);
+  k_draw_bwd2<<<persistent_grid(T, 12), 128, 0, st>>>(W, H, gx, T, reinterpret_cast<const int2 *>(ranges), recs,
+                                                      contrib, final_tau, dloss_dgammas, moments, tile_counter);
   GSB_CUDA_TRY(cudaGetLastError());
   return 0;
 }
