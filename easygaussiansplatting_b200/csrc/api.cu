@@ -255,6 +255,9 @@ int gsb_splat_render(int H, int W, int N, int64_t P, uint32_t depth_key_max, con
     GSB_REQUIRE(ws != nullptr && ws_bytes >= sizeof(int), "splat: workspace too small");
     tile_counter = static_cast<int *>(ws);
   }
+  // sparse frame (< 48 patches per tile on average): persistent grid + tile queue
+  const int64_t T = (int64_t)((W + GSB_TILE - 1) / GSB_TILE) * ((H + GSB_TILE - 1) / GSB_TILE);
+  if (P >= 48 * T) tile_counter = nullptr;
   return launch_draw(H, W, patch_range_per_tile, recs, image, contrib, final_tau, tile_counter, st);
 }
 
@@ -297,6 +300,8 @@ int gsb_splat_backward(int H, int W, int N, int64_t P, const float *us, const fl
     }
   }
   // P == 0: nothing was drawn; the zeroed moment rows finalise to all-zero gradients
+  const int64_t T = (int64_t)((W + GSB_TILE - 1) / GSB_TILE) * ((H + GSB_TILE - 1) / GSB_TILE);
+  if (P >= 48 * T) tile_counter = nullptr;  // dense frame: one CTA per tile
   return launch_draw_backward(H, W, N, patch_range_per_tile, P > 0 ? recs : nullptr, contrib, final_tau,
                               dloss_dgammas, cinv2ds, moments, tile_counter, dloss_dus, dloss_dcinv2ds,
                               dloss_dalphas, dloss_dcolors, st);

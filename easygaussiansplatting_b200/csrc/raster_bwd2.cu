@@ -66,9 +66,16 @@ __global__ void __launch_bounds__(128, 12) k_draw_bwd2(
 
   // persistent CTA: tiles are pulled from an atomic counter (see raster_fwd2.cu)
   for (int it = 0;; it++) {
-    if (tid == 0) s_tile[it & 1] = atomicAdd(tile_counter, 1);
-    __syncthreads();
-    const int tile = s_tile[it & 1];
+    int tile;
+    if (tile_counter != nullptr) {  // persistent grid: pull the next tile from the queue
+      if (tid == 0) s_tile[it & 1] = atomicAdd(tile_counter, 1);
+      __syncthreads();
+      tile = s_tile[it & 1];
+    } else {  // classic grid: one tile per CTA (dense frames: the hardware scheduler overlaps
+      if (it > 0) break;  // a CTA's start-up latency with its neighbours' compute)
+      __syncthreads();
+      tile = blockIdx.x;
+    }
     if (tile >= T) break;
     const int2 range = __ldg(ranges + tile);
     const int len = range.y - range.x;
@@ -189,9 +196,9 @@ int launch_draw_bwd2_kernel(int H, int W, const int32_t *ranges, const Rec *recs
                             int *tile_counter, cudaStream_t st) {
   const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
   const int T = gx * gy;
-  GSB_CUDA_TRY(cudaMemsetAsync(tile_counter, 0, sizeof(int), st));
+  if (tile_counter != nullptr) GSB_CUDA_TRY(cudaMemsetAsync(tile_counter, 0, sizeof(int), st));
   ProfScope ps(K_DRAW_BWD, st);
-  k_draw_bwd2<<<persistent_grid(T, 12), 128, 0, st>>>(W, H, gx, T, reinterpret_cast<const int2 *>(ranges), recs,
+  k_draw_bwd2<<<tile_counter != nullptr ? persistent_grid(T, 12) : T, 128, 0, st>>>(W, H, gx, T, reinterpret_cast<const int2 *>(ranges), recs,
                                                       contrib, final_tau, dloss_dgammas, moments, tile_counter);
   GSB_CUDA_TRY(cudaGetLastError());
   return 0;

@@ -8,9 +8,10 @@
 // pixel block, a CTA of 4 warps renders one 16x16 tile at a time, and the quadratic form, the
 // alpha multiply and the whole compositing update run as f32x2 operations on the pixel pair;
 // only min/max, ex2 and the compares stay scalar.
-// The grid is persistent (a few CTAs per SM) and pulls tile indices from an atomic counter, so
-// sparse frames (thousands of empty tiles: BASELINE config 4) are bounded by HBM writes, not
-// by CTA launch rate, and dense frames keep dynamic load balance.
+// For sparse frames (few patches per tile, thousands of empty tiles: the HBM-bound corner of
+// BASELINE config 4) the grid is persistent -- a few CTAs per SM pulling tile indices from an
+// atomic counter -- so the kernel is bounded by HBM writes instead of CTA launch rate; dense
+// frames use one CTA per tile (the caller passes tile_counter = nullptr).
 // The record pipeline (cp.async.bulk + mbarrier stages), the warp-level exact culling test and
 // the semantics (contrib, final_tau, thresholds) are the ones of raster_fwd.cu; per-pixel
 // arithmetic is the same sequence of IEEE operations, so both variants give identical images.
@@ -43,9 +44,16 @@ __global__ void __launch_bounds__(128) k_draw2(int W, int H, int gx, int T, cons
   uint32_t ph0 = 0, ph1 = 0;  // completed phases of the two stages (block-uniform)
 
   for (int it = 0;; it++) {
-    if (tid == 0) s_tile[it & 1] = atomicAdd(tile_counter, 1);
-    __syncthreads();
-    const int tile = s_tile[it & 1];
+    int tile;
+    if (tile_counter != nullptr) {  // persistent grid: pull the next tile from the queue
+      if (tid == 0) s_tile[it & 1] = atomicAdd(tile_counter, 1);
+      __syncthreads();
+      tile = s_tile[it & 1];
+    } else {  // classic grid: one tile per CTA (dense frames: the hardware scheduler overlaps
+      if (it > 0) break;  // a CTA's start-up latency with its neighbours' compute)
+      __syncthreads();
+      tile = blockIdx.x;
+    }
     if (tile >= T) break;
     const int tx = tile % gx, ty = tile / gx;
     // warp -> 8x8 block, lane -> (row, pixel pair)
@@ -171,9 +179,9 @@ int launch_draw2(int H, int W, const int32_t *ranges, const Rec *recs, float *im
   const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
   if (gx <= 0 || gy <= 0) return 0;
   const int T = gx * gy;
-  GSB_CUDA_TRY(cudaMemsetAsync(tile_counter, 0, sizeof(int), st));
+  if (tile_counter != nullptr) GSB_CUDA_TRY(cudaMemsetAsync(tile_counter, 0, sizeof(int), st));
   ProfScope ps(K_DRAW, st);
-  k_draw2<<<persistent_grid(T, 12), 128, 0, st>>>(W, H, gx, T, reinterpret_cast<const int2 *>(ranges), recs, image,
+  k_draw2<<<tile_counter != nullptr ? persistent_grid(T, 12) : T, 128, 0, st>>>(W, H, gx, T, reinterpret_cast<const int2 *>(ranges), recs, image,
                                                   contrib, final_tau, tile_counter);
   GSB_CUDA_TRY(cudaGetLastError());
   return 0;
