@@ -25,6 +25,7 @@ constexpr int DRAW2_BATCH = 128;
 __device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
 __device__ __forceinline__ float2 f2s(float a) { return make_float2(a, a); }
 
+template <bool PERSIST>
 __global__ void __launch_bounds__(128) k_draw2(int W, int H, int gx, int T, const int2 *__restrict__ ranges,
                                                const Rec *__restrict__ recs, float *__restrict__ image,
                                                int32_t *__restrict__ contrib, float *__restrict__ final_tau,
@@ -45,7 +46,7 @@ __global__ void __launch_bounds__(128) k_draw2(int W, int H, int gx, int T, cons
 
   for (int it = 0;; it++) {
     int tile;
-    if (tile_counter != nullptr) {  // persistent grid: pull the next tile from the queue
+    if (PERSIST) {  // persistent grid: pull the next tile from the queue
       if (tid == 0) s_tile[it & 1] = atomicAdd(tile_counter, 1);
       __syncthreads();
       tile = s_tile[it & 1];
@@ -87,7 +88,13 @@ __global__ void __launch_bounds__(128) k_draw2(int W, int H, int gx, int T, cons
       int b = 0;
       for (; b < nb; b++) {
         const int s = b & 1;
-        if (s == 0) { mbar_wait(&mbar[0], ph0 & 1); ph0++; } else { mbar_wait(&mbar[1], ph1 & 1); ph1++; }
+        if (!PERSIST) {
+          mbar_wait(&mbar[s], (b >> 1) & 1);  // one tile per CTA: the phase follows the batch index
+        } else if (s == 0) {
+          mbar_wait(&mbar[0], ph0 & 1); ph0++;
+        } else {
+          mbar_wait(&mbar[1], ph1 & 1); ph1++;
+        }
         const int nrec = min(DRAW2_BATCH, len - b * DRAW2_BATCH);
         if (!warp_done) {
           for (int c0 = 0; c0 < nrec; c0 += 32) {
@@ -141,7 +148,13 @@ __global__ void __launch_bounds__(128) k_draw2(int W, int H, int gx, int T, cons
       }
       // early exit: the next stage's bulk copy is in flight into shared memory -- consume it
       if (b + 1 < nb) {
-        if (((b + 1) & 1) == 0) { mbar_wait(&mbar[0], ph0 & 1); ph0++; } else { mbar_wait(&mbar[1], ph1 & 1); ph1++; }
+        if (!PERSIST) {
+          mbar_wait(&mbar[(b + 1) & 1], ((b + 1) >> 1) & 1);
+        } else if (((b + 1) & 1) == 0) {
+          mbar_wait(&mbar[0], ph0 & 1); ph0++;
+        } else {
+          mbar_wait(&mbar[1], ph1 & 1); ph1++;
+        }
       }
     }
     if (in0 && in1 && vec2) {
@@ -181,8 +194,12 @@ int launch_draw2(int H, int W, const int32_t *ranges, const Rec *recs, float *im
   const int T = gx * gy;
   if (tile_counter != nullptr) GSB_CUDA_TRY(cudaMemsetAsync(tile_counter, 0, sizeof(int), st));
   ProfScope ps(K_DRAW, st);
-  k_draw2<<<tile_counter != nullptr ? persistent_grid(T, 12) : T, 128, 0, st>>>(W, H, gx, T, reinterpret_cast<const int2 *>(ranges), recs, image,
-                                                  contrib, final_tau, tile_counter);
+  if (tile_counter != nullptr)
+    k_draw2<true><<<persistent_grid(T, 12), 128, 0, st>>>(W, H, gx, T, reinterpret_cast<const int2 *>(ranges), recs,
+                                                          image, contrib, final_tau, tile_counter);
+  else
+    k_draw2<false><<<T, 128, 0, st>>>(W, H, gx, T, reinterpret_cast<const int2 *>(ranges), recs, image, contrib,
+                                      final_tau, tile_counter);
   GSB_CUDA_TRY(cudaGetLastError());
   return 0;
 }
