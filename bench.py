@@ -318,6 +318,30 @@ def run_ours(args, rank, world):
                 "note": "draw/draw_backward are issue-bound on dense scenes (SURVEY 8d: ~140 flop/B); "
                         "profiles/ holds the ncu pipe utilisation and dram__bytes"}
 
+    # ---- training loss (row N2): fused gau_loss fwd+grad vs the torch chain it replaces
+    from easygaussiansplatting_b200.loss import gau_loss_with_grad
+    import torch.nn.functional as F
+    gt_img = (img.detach() + 0.05 * torch.randn_like(img)).clamp(0, 1)
+
+    def torch_loss():
+        x = img.detach().clone().requires_grad_()
+        g1 = torch.tensor([np.exp(-(k - 5) ** 2 / 4.5) for k in range(11)], dtype=torch.float32, device=dev)
+        g1 = (g1 / g1.sum()).unsqueeze(1)
+        win = g1.mm(g1.t()).unsqueeze(0).unsqueeze(0).expand(3, 1, 11, 11).contiguous()
+        mu1 = F.conv2d(x, win, padding=5, groups=3); mu2 = F.conv2d(gt_img, win, padding=5, groups=3)
+        s11 = F.conv2d(x * x, win, padding=5, groups=3) - mu1.pow(2)
+        s22 = F.conv2d(gt_img * gt_img, win, padding=5, groups=3) - mu2.pow(2)
+        s12 = F.conv2d(x * gt_img, win, padding=5, groups=3) - mu1 * mu2
+        ssim = ((2 * mu1 * mu2 + 1e-4) * (2 * s12 + 9e-4)) / ((mu1.pow(2) + mu2.pow(2) + 1e-4) * (s11 + s22 + 9e-4))
+        (0.8 * torch.abs(x - gt_img).mean() + 0.2 * (1 - ssim.mean())).backward()
+    ms_loss_fused = timed(lambda: gau_loss_with_grad(img, gt_img), 10, 3) / 10
+    ms_loss_torch = timed(torch_loss, 5, 2) / 5
+    loss_bytes = 132 * WH
+    loss_info = {"what": "gau_loss forward + dloss/dimage at 1920x1080 (pytorch_ssim.py:64-67 + autograd)",
+                 "fused_ms": ms_loss_fused, "torch_chain_ms": ms_loss_torch,
+                 "algorithmic_bytes": loss_bytes, "achieved_GBps": loss_bytes / (ms_loss_fused * 1e-3) / 1e9,
+                 "hbm_frac": loss_bytes / (ms_loss_fused * 1e-3) / 1e9 / peak}
+
     # ---- CPU baseline + gradient error vs the CPU oracle on the same crop
     cpu_mpix, cpu_sec, cpu_threads, cpu = cpu_sample(steps=1, warmup=0)
     err = gpu_vs_cpu_crop(torch, dev, cpu)
@@ -341,6 +365,7 @@ def run_ours(args, rank, world):
         "grad_max_rel_err_vs_cpu": err["grad_max_rel_err"], "parity_vs_cpu": err,
         "roofline": roofline,
         "kernel_ms_per_step": kern,
+        "loss_n2": loss_info,
         "cpu_baseline": {"value": cpu_mpix, "unit": "Mpixels/s", "cores": cpu_threads, "kind": "port",
                          "sample": sample_text(cpu_sec)},
         "e2e": {"value": e2e, "unit": "Mpixels/s", "ms_per_step": ms_e2e / args.steps,

@@ -28,6 +28,8 @@ SIGNATURES = {
     "gsb_splat_backward_workspace_bytes": (_sz, [_i, _i, _i, _i64]),
     "gsb_splat_backward": (_i, [_i, _i, _i, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                 _sz, _vp, _vp, _vp, _vp, _vp]),
+    "gsb_gau_loss_workspace_bytes": (_sz, [_i, _i]),
+    "gsb_gau_loss": (_i, [_i, _i, _vp, _vp, _f, _vp, _vp, _vp, _sz, _vp]),
     "gsb_set_option": (_i, [C.c_char_p, _i]),
     "gsb_profile_enable": (None, [_i]),
     "gsb_profile_kernels": (_i, []),

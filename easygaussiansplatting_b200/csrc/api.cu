@@ -44,7 +44,7 @@ static const char *const g_names[K_COUNT] = {"project", "computeCov3D", "compute
                                              "inverseCov2D", "rects", "scan(cub)", "keys", "sort(cub)",
                                              "ranges", "pack_records", "draw", "draw_backward",
                                              "preprocess_forward", "preprocess_backward",
-                                             "finalize_splat_grads"};
+                                             "finalize_splat_grads", "gau_loss_forward", "gau_loss_backward"};
 
 ProfScope::ProfScope(int id, cudaStream_t st) : id_(id), st_(st), stop_(nullptr) {
   std::lock_guard<std::mutex> lk(g_prof_mu);
@@ -193,6 +193,16 @@ int gsb_preprocess_backward(int N, int sh_dim3, const float *pws, const float *r
   return launch_preprocess_bwd(N, sh_dim3, pws, rots, scales, shs, Rcw, tcw, twc, fx, fy, cx, cy, width, height,
                                dloss_dus, dloss_dcinv2ds, dloss_dcolors, dloss_dpws, dloss_dshs, dloss_dscales,
                                dloss_drots, (cudaStream_t)stream);
+}
+
+size_t gsb_gau_loss_workspace_bytes(int H, int W) { return gau_loss_workspace_bytes(H, W); }
+
+int gsb_gau_loss(int H, int W, const float *image, const float *gt_image, float loss_lambda, float *loss_out,
+                 float *dloss_dimage, void *ws, size_t ws_bytes, gsb_stream_t stream) {
+  GSB_REQUIRE(H > 0 && W > 0, "gau_loss: bad H/W");
+  GSB_REQUIRE(image && gt_image && loss_out && ws, "gau_loss: null pointer");
+  GSB_REQUIRE(ws_bytes >= gau_loss_workspace_bytes(H, W), "gau_loss: workspace too small");
+  return launch_gau_loss(H, W, image, gt_image, loss_lambda, loss_out, dloss_dimage, ws, (cudaStream_t)stream);
 }
 
 size_t gsb_splat_bin_workspace_bytes(int N) { return bin_layout(N).bytes; }

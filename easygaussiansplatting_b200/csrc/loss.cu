@@ -1,0 +1,182 @@
+// Fused training loss: gau_loss = (1-l) mean|img - gt| + l (1 - mean SSIM),
+// replacing the reference's five depthwise 11x11 F.conv2d + elementwise chain and its autograd
+// backward (gsplat/pytorch_ssim.py:26-67) with two HBM-bound kernels:
+//   k_ssim_fwd : separable 11-tap Gaussian (sigma 1.5, zero padding) of img, gt, img^2, gt^2,
+//                img*gt in shared memory -> SSIM map, L1 and SSIM sums (one double atomicAdd
+//                per CTA), and the three partial-derivative maps dSSIM/d{mu1, E11, E12};
+//   k_ssim_bwd : the same separable filter over the three maps, combined with img / gt and the
+//                L1 sign into dloss/dimg -- exactly what loss.backward() hands to splatB --
+//                and the final loss scalar.
+// Algorithmic bytes: 24 (read img, gt) + 36 (write maps) + 36 + 24 (read) + 12 (write grad)
+// = 132 B per pixel (x3 channels already counted) -> HBM roofline.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace gsb {
+
+constexpr int LW = 32, LH = 16, LR = 5;              // output tile, filter radius
+constexpr int LIW = LW + 2 * LR, LIH = LH + 2 * LR;  // 42 x 26 input region
+struct Win11 { float w[11]; };
+
+__global__ void __launch_bounds__(256) k_ssim_fwd(int W, int H, const float *__restrict__ img,
+                                                  const float *__restrict__ gt, Win11 win,
+                                                  float *__restrict__ maps /* [3 maps][3][H][W] */,
+                                                  double *__restrict__ acc /* [l1 sum, ssim sum] */) {
+  __shared__ float s1[LIH][LIW + 1], s2[LIH][LIW + 1];
+  __shared__ float hs[5][LIH][LW + 1];
+  __shared__ float red[2][8];
+  const int tid = threadIdx.x;
+  const int x0 = blockIdx.x * LW, y0 = blockIdx.y * LH, c = blockIdx.z;
+  const size_t HW = (size_t)H * W;
+  const float *a = img + (size_t)c * HW, *b = gt + (size_t)c * HW;
+  for (int i = tid; i < LIH * LIW; i += 256) {
+    const int r = i / LIW, q = i % LIW;
+    const int y = y0 + r - LR, x = x0 + q - LR;
+    const bool in = (x >= 0) && (x < W) && (y >= 0) && (y < H);
+    s1[r][q] = in ? __ldg(a + (size_t)y * W + x) : 0.f;
+    s2[r][q] = in ? __ldg(b + (size_t)y * W + x) : 0.f;
+  }
+  __syncthreads();
+  for (int i = tid; i < LIH * LW; i += 256) {
+    const int r = i / LW, q = i % LW;
+    float m1 = 0.f, m2 = 0.f, e11 = 0.f, e22 = 0.f, e12 = 0.f;
+#pragma unroll
+    for (int k = 0; k < 11; k++) {
+      const float w = win.w[k], p = s1[r][q + k], g = s2[r][q + k];
+      m1 = fmaf(w, p, m1); m2 = fmaf(w, g, m2);
+      e11 = fmaf(w * p, p, e11); e22 = fmaf(w * g, g, e22); e12 = fmaf(w * p, g, e12);
+    }
+    hs[0][r][q] = m1; hs[1][r][q] = m2; hs[2][r][q] = e11; hs[3][r][q] = e22; hs[4][r][q] = e12;
+  }
+  __syncthreads();
+  const float C1 = 0.01f * 0.01f, C2 = 0.03f * 0.03f;
+  float l1 = 0.f, ss = 0.f;
+  for (int i = tid; i < LH * LW; i += 256) {
+    const int r = i / LW, q = i % LW;
+    const int y = y0 + r, x = x0 + q;
+    if (x >= W || y >= H) continue;
+    float v[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < 11; k++) {
+      const float w = win.w[k];
+#pragma unroll
+      for (int j = 0; j < 5; j++) v[j] = fmaf(w, hs[j][r + k][q], v[j]);
+    }
+    const float mu1 = v[0], mu2 = v[1];
+    const float s11 = v[2] - mu1 * mu1, s22 = v[3] - mu2 * mu2, s12 = v[4] - mu1 * mu2;
+    const float A1 = 2.f * mu1 * mu2 + C1, A2 = 2.f * s12 + C2;
+    const float B1 = mu1 * mu1 + mu2 * mu2 + C1, B2 = s11 + s22 + C2;
+    const float inv = 1.0f / (B1 * B2);
+    const float ssim = A1 * A2 * inv;
+    ss += ssim;
+    l1 += fabsf(s1[r + LR][q + LR] - s2[r + LR][q + LR]);
+    const size_t o = (size_t)c * HW + (size_t)y * W + x;
+    maps[o] = (2.f * mu2 * (A2 - A1)) * inv - ssim * (2.f * mu1 * (B2 - B1)) * inv;  // dSSIM/dmu1
+    maps[3 * HW + o] = -ssim / B2;                                                    // dSSIM/dE11
+    maps[6 * HW + o] = 2.f * A1 * inv;                                                // dSSIM/dE12
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    l1 += __shfl_xor_sync(0xffffffffu, l1, o);
+    ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  }
+  if ((tid & 31) == 0) { red[0][tid >> 5] = l1; red[1][tid >> 5] = ss; }
+  __syncthreads();
+  if (tid == 0) {
+    double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) { a0 += (double)red[0][w]; a1 += (double)red[1][w]; }
+    atomicAdd(acc + 0, a0);
+    atomicAdd(acc + 1, a1);
+  }
+}
+
+__global__ void __launch_bounds__(256) k_ssim_bwd(int W, int H, const float *__restrict__ img,
+                                                  const float *__restrict__ gt, Win11 win,
+                                                  const float *__restrict__ maps, const double *__restrict__ acc,
+                                                  float lambda, float *__restrict__ loss_out,
+                                                  float *__restrict__ grad /* [3,H,W] or nullptr */) {
+  __shared__ float sm[3][LIH][LIW + 1];
+  __shared__ float hs[3][LIH][LW + 1];
+  const int tid = threadIdx.x;
+  const int x0 = blockIdx.x * LW, y0 = blockIdx.y * LH, c = blockIdx.z;
+  const size_t HW = (size_t)H * W;
+  const double n = 3.0 * (double)HW;
+  if (blockIdx.x == 0 && blockIdx.y == 0 && c == 0 && tid == 0)
+    *loss_out = (float)((1.0 - (double)lambda) * (acc[0] / n) + (double)lambda * (1.0 - acc[1] / n));
+  if (grad == nullptr) return;
+  for (int i = tid; i < LIH * LIW; i += 256) {
+    const int r = i / LIW, q = i % LIW;
+    const int y = y0 + r - LR, x = x0 + q - LR;
+    const bool in = (x >= 0) && (x < W) && (y >= 0) && (y < H);
+    const size_t o = (size_t)c * HW + (size_t)(in ? y : 0) * W + (in ? x : 0);
+#pragma unroll
+    for (int m = 0; m < 3; m++) sm[m][r][q] = in ? __ldg(maps + 3 * m * HW + o) : 0.f;
+  }
+  __syncthreads();
+  for (int i = tid; i < LIH * LW; i += 256) {
+    const int r = i / LW, q = i % LW;
+    float v[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < 11; k++) {
+      const float w = win.w[k];
+#pragma unroll
+      for (int m = 0; m < 3; m++) v[m] = fmaf(w, sm[m][r][q + k], v[m]);
+    }
+#pragma unroll
+    for (int m = 0; m < 3; m++) hs[m][r][q] = v[m];
+  }
+  __syncthreads();
+  const float inv_n = (float)(1.0 / n);
+  for (int i = tid; i < LH * LW; i += 256) {
+    const int r = i / LW, q = i % LW;
+    const int y = y0 + r, x = x0 + q;
+    if (x >= W || y >= H) continue;
+    float v[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < 11; k++) {
+      const float w = win.w[k];
+#pragma unroll
+      for (int m = 0; m < 3; m++) v[m] = fmaf(w, hs[m][r + k][q], v[m]);
+    }
+    const size_t o = (size_t)c * HW + (size_t)y * W + x;
+    const float p = __ldg(img + o), g = __ldg(gt + o);
+    const float sgn = (p > g) ? 1.f : ((p < g) ? -1.f : 0.f);
+    grad[o] = (1.f - lambda) * sgn * inv_n - lambda * inv_n * (v[0] + 2.f * p * v[1] + g * v[2]);
+  }
+}
+
+size_t gau_loss_workspace_bytes(int H, int W) {
+  return 256 + (size_t)9 * H * W * sizeof(float);  // [2 doubles, padded] [3 maps x 3 channels]
+}
+
+int launch_gau_loss(int H, int W, const float *img, const float *gt, float lambda, float *loss_out,
+                    float *grad, void *ws, cudaStream_t st) {
+  if (H <= 0 || W <= 0) return set_arg_error("gau_loss: bad image size");
+  Win11 win;
+  {  // gsplat/pytorch_ssim.py:12-15: float32 taps, float32 normalisation
+    float s = 0.f;
+    for (int x = 0; x < 11; x++) {
+      win.w[x] = (float)exp(-(double)((x - 5) * (x - 5)) / (2.0 * 1.5 * 1.5));
+      s += win.w[x];
+    }
+    for (int x = 0; x < 11; x++) win.w[x] /= s;
+  }
+  double *acc = static_cast<double *>(ws);
+  float *maps = reinterpret_cast<float *>(static_cast<char *>(ws) + 256);
+  GSB_CUDA_TRY(cudaMemsetAsync(acc, 0, 2 * sizeof(double), st));
+  const dim3 grid((W + LW - 1) / LW, (H + LH - 1) / LH, 3);
+  {
+    ProfScope ps(K_LOSS_FWD, st);
+    k_ssim_fwd<<<grid, 256, 0, st>>>(W, H, img, gt, win, maps, acc);
+  }
+  GSB_CUDA_TRY(cudaGetLastError());
+  {
+    ProfScope ps(K_LOSS_BWD, st);
+    k_ssim_bwd<<<grid, 256, 0, st>>>(W, H, img, gt, win, maps, acc, lambda, loss_out, grad);
+  }
+  GSB_CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace gsb

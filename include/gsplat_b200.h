@@ -141,6 +141,16 @@ int gsb_splat_backward(int H, int W, int N, int64_t P, const float *us, const fl
                        size_t ws_bytes, float *dloss_dus, float *dloss_dcinv2ds,
                        float *dloss_dalphas, float *dloss_dcolors, gsb_stream_t stream);
 
+/* ---- training loss (extension).  Replaces `gau_loss`
+ * (gsplat/pytorch_ssim.py:64-67, called at train.py:52) and its autograd backward:
+ *   loss = (1 - lambda) mean|image - gt| + lambda (1 - mean SSIM), 11x11 Gaussian window
+ *   (sigma 1.5), zero padding, C1 = 0.01^2, C2 = 0.03^2, image/gt [3,H,W] planar f32.
+ * Writes the scalar loss to *loss_out (device) and, if dloss_dimage != NULL, dloss/dimage
+ * [3,H,W] -- the tensor loss.backward() would hand to splatB. */
+size_t gsb_gau_loss_workspace_bytes(int H, int W);
+int gsb_gau_loss(int H, int W, const float *image, const float *gt_image, float loss_lambda, float *loss_out,
+                 float *dloss_dimage, void *ws, size_t ws_bytes, gsb_stream_t stream);
+
 /* ---- options.  "raster_variant": 2 (default) = two pixels per lane with packed f32x2
  * arithmetic (FFMA2/FMUL2/FADD2), 1 = one pixel per lane; same results, kept for A/B
  * measurements.  Also read once from the environment variable GSB_RASTER_VARIANT. */

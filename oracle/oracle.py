@@ -196,3 +196,25 @@ def chain_backward(Rcw, dloss_dus, dloss_dcinv2ds, dloss_dalphas, dloss_dcolors,
     dpws = dus @ f(du_dpcs) @ R + dco @ f(dcolor_dpws) + dcov2d @ f(dcov2d_dpcs) @ R
     return dict(pws=dpws[:, 0], shs=dshs, alphas=dal[:, 0], scales=dscales[:, 0],
                 rots=drots[:, 0], us=dus[:, 0])
+
+
+# ---------------------------------------------------------------- training loss (row N2)
+def ssim_window():
+    """gsplat/pytorch_ssim.py:12-15: 11 taps, sigma 1.5, built and normalised in float32"""
+    g = np.array([np.exp(-(x - 5) ** 2 / float(2 * 1.5 ** 2)) for x in range(11)], dtype=np.float32)
+    return (g / g.sum(dtype=np.float32)).astype(np.float64)
+
+
+def gau_loss(image, gt, loss_lambda=0.2, want_grad=True):
+    """gsplat/pytorch_ssim.py:64-67 (+ its autograd gradient).  image, gt: [3,H,W] float32.
+    -> dict(loss, l1, ssim, dloss_dimage[3,H,W] f64)"""
+    image, gt = _f32(image), _f32(gt)
+    assert image.shape == gt.shape and image.ndim == 3
+    Cn, H, W = image.shape
+    assert Cn == 3
+    win = ssim_window()
+    loss, l1, ss = C.c_double(0), C.c_double(0), C.c_double(0)
+    grad = np.empty((3, H, W)) if want_grad else None
+    lib().orc_gau_loss(H, W, _p(image), _p(gt), C.c_double(loss_lambda), _p(win), C.byref(loss), C.byref(l1),
+                       C.byref(ss), _p(grad))
+    return dict(loss=loss.value, l1=l1.value, ssim=ss.value, dloss_dimage=grad)
