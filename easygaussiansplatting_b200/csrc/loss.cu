@@ -37,43 +37,62 @@ __global__ void __launch_bounds__(256) k_ssim_fwd(int W, int H, const float *__r
     s2[r][q] = in ? __ldg(b + (size_t)y * W + x) : 0.f;
   }
   __syncthreads();
-  for (int i = tid; i < LIH * LW; i += 256) {
-    const int r = i / LW, q = i % LW;
-    float m1 = 0.f, m2 = 0.f, e11 = 0.f, e22 = 0.f, e12 = 0.f;
+  // horizontal pass, register blocked: one thread = 4 consecutive outputs of a row, so the 14
+  // inputs they share are read from shared memory once (the kernel is LDS-bound otherwise)
+  for (int i = tid; i < LIH * (LW / 4); i += 256) {
+    const int r = i / (LW / 4), q0 = 4 * (i % (LW / 4));
+    float p[14], g[14];
 #pragma unroll
-    for (int k = 0; k < 11; k++) {
-      const float w = win.w[k], p = s1[r][q + k], g = s2[r][q + k];
-      m1 = fmaf(w, p, m1); m2 = fmaf(w, g, m2);
-      e11 = fmaf(w * p, p, e11); e22 = fmaf(w * g, g, e22); e12 = fmaf(w * p, g, e12);
+    for (int k = 0; k < 14; k++) { p[k] = s1[r][q0 + k]; g[k] = s2[r][q0 + k]; }
+#pragma unroll
+    for (int m = 0; m < 4; m++) {
+      float m1 = 0.f, m2 = 0.f, e11 = 0.f, e22 = 0.f, e12 = 0.f;
+#pragma unroll
+      for (int k = 0; k < 11; k++) {
+        const float w = win.w[k], a = p[m + k], b2 = g[m + k];
+        m1 = fmaf(w, a, m1); m2 = fmaf(w, b2, m2);
+        e11 = fmaf(w * a, a, e11); e22 = fmaf(w * b2, b2, e22); e12 = fmaf(w * a, b2, e12);
+      }
+      hs[0][r][q0 + m] = m1; hs[1][r][q0 + m] = m2; hs[2][r][q0 + m] = e11; hs[3][r][q0 + m] = e22;
+      hs[4][r][q0 + m] = e12;
     }
-    hs[0][r][q] = m1; hs[1][r][q] = m2; hs[2][r][q] = e11; hs[3][r][q] = e22; hs[4][r][q] = e12;
   }
   __syncthreads();
   const float C1 = 0.01f * 0.01f, C2 = 0.03f * 0.03f;
   float l1 = 0.f, ss = 0.f;
-  for (int i = tid; i < LH * LW; i += 256) {
-    const int r = i / LW, q = i % LW;
-    const int y = y0 + r, x = x0 + q;
-    if (x >= W || y >= H) continue;
-    float v[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+  // vertical pass, register blocked: one thread = 2 consecutive rows of a column
+  for (int i = tid; i < (LH / 2) * LW; i += 256) {
+    const int r0 = 2 * (i / LW), q = i % LW;
+    const int x = x0 + q;
+    float col[5][12];
 #pragma unroll
-    for (int k = 0; k < 11; k++) {
-      const float w = win.w[k];
+    for (int j = 0; j < 5; j++)
 #pragma unroll
-      for (int j = 0; j < 5; j++) v[j] = fmaf(w, hs[j][r + k][q], v[j]);
+      for (int k = 0; k < 12; k++) col[j][k] = hs[j][r0 + k][q];
+#pragma unroll
+    for (int m = 0; m < 2; m++) {
+      const int r = r0 + m, y = y0 + r;
+      if (x >= W || y >= H) continue;
+      float v[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int k = 0; k < 11; k++) {
+        const float w = win.w[k];
+#pragma unroll
+        for (int j = 0; j < 5; j++) v[j] = fmaf(w, col[j][m + k], v[j]);
+      }
+      const float mu1 = v[0], mu2 = v[1];
+      const float s11 = v[2] - mu1 * mu1, s22 = v[3] - mu2 * mu2, s12 = v[4] - mu1 * mu2;
+      const float A1 = 2.f * mu1 * mu2 + C1, A2 = 2.f * s12 + C2;
+      const float B1 = mu1 * mu1 + mu2 * mu2 + C1, B2 = s11 + s22 + C2;
+      const float inv = 1.0f / (B1 * B2);
+      const float ssim = A1 * A2 * inv;
+      ss += ssim;
+      l1 += fabsf(s1[r + LR][q + LR] - s2[r + LR][q + LR]);
+      const size_t o = (size_t)c * HW + (size_t)y * W + x;
+      maps[o] = (2.f * mu2 * (A2 - A1)) * inv - ssim * (2.f * mu1 * (B2 - B1)) * inv;  // dSSIM/dmu1
+      maps[3 * HW + o] = -ssim / B2;                                                    // dSSIM/dE11
+      maps[6 * HW + o] = 2.f * A1 * inv;                                                // dSSIM/dE12
     }
-    const float mu1 = v[0], mu2 = v[1];
-    const float s11 = v[2] - mu1 * mu1, s22 = v[3] - mu2 * mu2, s12 = v[4] - mu1 * mu2;
-    const float A1 = 2.f * mu1 * mu2 + C1, A2 = 2.f * s12 + C2;
-    const float B1 = mu1 * mu1 + mu2 * mu2 + C1, B2 = s11 + s22 + C2;
-    const float inv = 1.0f / (B1 * B2);
-    const float ssim = A1 * A2 * inv;
-    ss += ssim;
-    l1 += fabsf(s1[r + LR][q + LR] - s2[r + LR][q + LR]);
-    const size_t o = (size_t)c * HW + (size_t)y * W + x;
-    maps[o] = (2.f * mu2 * (A2 - A1)) * inv - ssim * (2.f * mu1 * (B2 - B1)) * inv;  // dSSIM/dmu1
-    maps[3 * HW + o] = -ssim / B2;                                                    // dSSIM/dE11
-    maps[6 * HW + o] = 2.f * A1 * inv;                                                // dSSIM/dE12
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -114,35 +133,52 @@ __global__ void __launch_bounds__(256) k_ssim_bwd(int W, int H, const float *__r
     for (int m = 0; m < 3; m++) sm[m][r][q] = in ? __ldg(maps + 3 * m * HW + o) : 0.f;
   }
   __syncthreads();
-  for (int i = tid; i < LIH * LW; i += 256) {
-    const int r = i / LW, q = i % LW;
-    float v[3] = {0.f, 0.f, 0.f};
+  for (int i = tid; i < LIH * (LW / 4); i += 256) {  // 4 outputs per thread (see k_ssim_fwd)
+    const int r = i / (LW / 4), q0 = 4 * (i % (LW / 4));
+    float in[3][14];
 #pragma unroll
-    for (int k = 0; k < 11; k++) {
-      const float w = win.w[k];
+    for (int m = 0; m < 3; m++)
 #pragma unroll
-      for (int m = 0; m < 3; m++) v[m] = fmaf(w, sm[m][r][q + k], v[m]);
+      for (int k = 0; k < 14; k++) in[m][k] = sm[m][r][q0 + k];
+#pragma unroll
+    for (int t = 0; t < 4; t++) {
+      float v[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+      for (int k = 0; k < 11; k++) {
+        const float w = win.w[k];
+#pragma unroll
+        for (int m = 0; m < 3; m++) v[m] = fmaf(w, in[m][t + k], v[m]);
+      }
+#pragma unroll
+      for (int m = 0; m < 3; m++) hs[m][r][q0 + t] = v[m];
     }
-#pragma unroll
-    for (int m = 0; m < 3; m++) hs[m][r][q] = v[m];
   }
   __syncthreads();
   const float inv_n = (float)(1.0 / n);
-  for (int i = tid; i < LH * LW; i += 256) {
-    const int r = i / LW, q = i % LW;
-    const int y = y0 + r, x = x0 + q;
-    if (x >= W || y >= H) continue;
-    float v[3] = {0.f, 0.f, 0.f};
+  for (int i = tid; i < (LH / 2) * LW; i += 256) {  // 2 rows per thread
+    const int r0 = 2 * (i / LW), q = i % LW;
+    const int x = x0 + q;
+    float col[3][12];
 #pragma unroll
-    for (int k = 0; k < 11; k++) {
-      const float w = win.w[k];
+    for (int m = 0; m < 3; m++)
 #pragma unroll
-      for (int m = 0; m < 3; m++) v[m] = fmaf(w, hs[m][r + k][q], v[m]);
+      for (int k = 0; k < 12; k++) col[m][k] = hs[m][r0 + k][q];
+#pragma unroll
+    for (int t = 0; t < 2; t++) {
+      const int y = y0 + r0 + t;
+      if (x >= W || y >= H) continue;
+      float v[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+      for (int k = 0; k < 11; k++) {
+        const float w = win.w[k];
+#pragma unroll
+        for (int m = 0; m < 3; m++) v[m] = fmaf(w, col[m][t + k], v[m]);
+      }
+      const size_t o = (size_t)c * HW + (size_t)y * W + x;
+      const float p = __ldg(img + o), g = __ldg(gt + o);
+      const float sgn = (p > g) ? 1.f : ((p < g) ? -1.f : 0.f);
+      grad[o] = (1.f - lambda) * sgn * inv_n - lambda * inv_n * (v[0] + 2.f * p * v[1] + g * v[2]);
     }
-    const size_t o = (size_t)c * HW + (size_t)y * W + x;
-    const float p = __ldg(img + o), g = __ldg(gt + o);
-    const float sgn = (p > g) ? 1.f : ((p < g) ? -1.f : 0.f);
-    grad[o] = (1.f - lambda) * sgn * inv_n - lambda * inv_n * (v[0] + 2.f * p * v[1] + g * v[2]);
   }
 }
 
