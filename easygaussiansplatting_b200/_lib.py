@@ -28,6 +28,7 @@ SIGNATURES = {
     "gsb_splat_backward_workspace_bytes": (_sz, [_i, _i, _i, _i64]),
     "gsb_splat_backward": (_i, [_i, _i, _i, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                 _sz, _vp, _vp, _vp, _vp, _vp]),
+    "gsb_small_bmm": (_i, [C.c_longlong, _i, _i, _i, _vp, _vp, _i, _vp, _vp]),
     "gsb_gau_loss_workspace_bytes": (_sz, [_i, _i]),
     "gsb_gau_loss": (_i, [_i, _i, _vp, _vp, _f, _vp, _vp, _vp, _sz, _vp]),
     "gsb_set_option": (_i, [C.c_char_p, _i]),

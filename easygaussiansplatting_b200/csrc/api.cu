@@ -44,7 +44,8 @@ static const char *const g_names[K_COUNT] = {"project", "computeCov3D", "compute
                                              "inverseCov2D", "rects", "scan(cub)", "keys", "sort(cub)",
                                              "ranges", "pack_records", "draw", "draw_backward",
                                              "preprocess_forward", "preprocess_backward",
-                                             "finalize_splat_grads", "gau_loss_forward", "gau_loss_backward"};
+                                             "finalize_splat_grads", "gau_loss_forward", "gau_loss_backward",
+                                             "small_bmm"};
 
 ProfScope::ProfScope(int id, cudaStream_t st) : id_(id), st_(st), stop_(nullptr) {
   std::lock_guard<std::mutex> lk(g_prof_mu);
@@ -193,6 +194,13 @@ int gsb_preprocess_backward(int N, int sh_dim3, const float *pws, const float *r
   return launch_preprocess_bwd(N, sh_dim3, pws, rots, scales, shs, Rcw, tcw, twc, fx, fy, cx, cy, width, height,
                                dloss_dus, dloss_dcinv2ds, dloss_dcolors, dloss_dpws, dloss_dshs, dloss_dscales,
                                dloss_drots, (cudaStream_t)stream);
+}
+
+int gsb_small_bmm(long long batch, int m, int k, int n, const float *A, const float *B, int b_shared, float *C,
+                  gsb_stream_t stream) {
+  GSB_REQUIRE(batch >= 0 && m > 0 && k > 0 && n > 0, "small_bmm: bad shape");
+  GSB_REQUIRE(batch == 0 || (A && B && C), "small_bmm: null pointer");
+  return launch_small_bmm(batch, m, k, n, A, B, b_shared, C, (cudaStream_t)stream);
 }
 
 size_t gsb_gau_loss_workspace_bytes(int H, int W) { return gau_loss_workspace_bytes(H, W); }

@@ -13,7 +13,7 @@ struct Rec;
 // gsb_profile_enable(1) is in effect (bench.py's roofline leg).
 enum KernelId {
   K_PROJECT = 0, K_COV3D, K_COV2D, K_SH2COLOR, K_INVCOV, K_RECTS, K_SCAN, K_KEYS, K_SORT, K_RANGES,
-  K_PACK, K_DRAW, K_DRAW_BWD, K_PRE_FWD, K_PRE_BWD, K_FINALIZE, K_LOSS_FWD, K_LOSS_BWD, K_COUNT
+  K_PACK, K_DRAW, K_DRAW_BWD, K_PRE_FWD, K_PRE_BWD, K_FINALIZE, K_LOSS_FWD, K_LOSS_BWD, K_BMM, K_COUNT
 };
 struct ProfScope {
   ProfScope(int id, cudaStream_t st);
@@ -46,6 +46,10 @@ int launch_preprocess_bwd(int N, int k3, const float *pws, const float *rots, co
                           float fy, float cx, float cy, float width, float height, const float *g_us,
                           const float *g_cinv2ds, const float *g_colors, float *g_pws, float *g_shs,
                           float *g_scales, float *g_rots, cudaStream_t st);
+
+// ---- batched tiny matmul for the reference's Jacobian chain (smallbmm.cu)
+int launch_small_bmm(long long batch, int M, int K, int NN, const float *A, const float *B, int b_shared,
+                     float *C, cudaStream_t st);
 
 // ---- fused training loss (loss.cu)
 size_t gau_loss_workspace_bytes(int H, int W);

@@ -16,6 +16,7 @@ import ctypes as C
 import torch
 
 from . import _lib
+from .jacobian_tensor import wrap as _jac
 
 _lib_handle = None
 
@@ -71,7 +72,7 @@ def project(pws, Rcw, tcw, focal_x, focal_y, center_x, center_y, calc_J):
         _lib.check(lib.gsb_project(N, _ptr(pws), _ptr(Rcw), _ptr(tcw), float(focal_x), float(focal_y),
                                    float(center_x), float(center_y), _ptr(us), _ptr(pcs), _ptr(depths),
                                    _ptr(J), _stream()), lib)
-    return [us, pcs, depths, J] if calc_J else [us, pcs, depths]
+    return [us, pcs, depths, _jac(J)] if calc_J else [us, pcs, depths]
 
 
 def computeCov3D(rots, scales, depths, calc_J):
@@ -90,7 +91,7 @@ def computeCov3D(rots, scales, depths, calc_J):
     with torch.cuda.device(rots.device):
         _lib.check(lib.gsb_compute_cov3d(N, _ptr(rots), _ptr(scales), _ptr(depths), _ptr(cov), _ptr(Jr),
                                          _ptr(Js), _stream()), lib)
-    return [cov, Jr, Js] if calc_J else [cov]
+    return [cov, _jac(Jr), _jac(Js)] if calc_J else [cov]
 
 
 def computeCov2D(cov3ds, pcs, Rcw, depths, focal_x, focal_y, width, height, calc_J):
@@ -110,7 +111,7 @@ def computeCov2D(cov3ds, pcs, Rcw, depths, focal_x, focal_y, width, height, calc
         _lib.check(lib.gsb_compute_cov2d(N, _ptr(cov3ds), _ptr(pcs), _ptr(Rcw), _ptr(depths),
                                          float(focal_x), float(focal_y), float(width), float(height),
                                          _ptr(cov), _ptr(Jc), _ptr(Jp), _stream()), lib)
-    return [cov, Jc, Jp] if calc_J else [cov]
+    return [cov, _jac(Jc), _jac(Jp)] if calc_J else [cov]
 
 
 def sh2Color(shs, pws, twc, calc_J):
@@ -132,7 +133,7 @@ def sh2Color(shs, pws, twc, calc_J):
     with torch.cuda.device(pws.device):
         _lib.check(lib.gsb_sh2color(N, k, _ptr(shs), _ptr(pws), _ptr(twc), _ptr(col), _ptr(Js), _ptr(Jp),
                                     _stream()), lib)
-    return [col, Js, Jp] if calc_J else [col]
+    return [col, _jac(Js), _jac(Jp)] if calc_J else [col]
 
 
 def inverseCov2D(cov2ds, depths, calc_J):
@@ -151,7 +152,7 @@ def inverseCov2D(cov2ds, depths, calc_J):
     with torch.cuda.device(cov2ds.device):
         _lib.check(lib.gsb_inverse_cov2d(N, _ptr(cov2ds), _ptr(depths), _ptr(cinv), _ptr(areas), _ptr(J),
                                          _stream()), lib)
-    return [cinv, areas, J] if calc_J else [cinv, areas]
+    return [cinv, areas, _jac(J)] if calc_J else [cinv, areas]
 
 
 def splat(height, width, us, cinv2ds, alphas, depths, colors, areas):
@@ -270,7 +271,8 @@ def splatB(height, width, us, cinv2ds, alphas, depths, colors, contrib, final_ta
                                           _ptr(contrib), _ptr(final_tau), _ptr(ranges), _ptr(gsid), _ptr(dl),
                                           recs, _ptr(ws), ws_bytes, _ptr(du), _ptr(dc), _ptr(da), _ptr(dcol),
                                           _stream()), lib)
-    return [du, dc, da, dcol]
+    # tagged so that the reference's `dloss_d* @ jacobian` chain takes the streaming matmul
+    return [_jac(du), _jac(dc), _jac(da), _jac(dcol)]
 
 
 # ---------------------------------------------------------------------------------------

@@ -141,6 +141,14 @@ int gsb_splat_backward(int H, int W, int N, int64_t P, const float *us, const fl
                        size_t ws_bytes, float *dloss_dus, float *dloss_dcinv2ds,
                        float *dloss_dalphas, float *dloss_dcolors, gsb_stream_t stream);
 
+/* ---- batched tiny matmul (extension).  C[b] = A[b] (m x k) . B[b] (k x n), or B shared by all
+ * batches when b_shared != 0; dense row-major f32.  This is the product the reference's
+ * GSFunction.backward applies ~12 times over the per-Gaussian Jacobians (gsmodel.py:72-85);
+ * ops.py routes torch.matmul on the Jacobian tensors it returns to this entry point so the
+ * unmodified reference chain runs at HBM speed instead of through batched-GEMV library calls. */
+int gsb_small_bmm(long long batch, int m, int k, int n, const float *A, const float *B, int b_shared, float *C,
+                  gsb_stream_t stream);
+
 /* ---- training loss (extension).  Replaces `gau_loss`
  * (gsplat/pytorch_ssim.py:64-67, called at train.py:52) and its autograd backward:
  *   loss = (1 - lambda) mean|image - gt| + lambda (1 - mean SSIM), 11x11 Gaussian window
