@@ -358,8 +358,9 @@ def run_ours(args, rank, world):
                    "l2": "per-step working set (params+grads 0.47 GB, records 0.12 GB, sort buffers) > 126 MB L2; "
                          "no explicit flush"},
         "gaussians_per_s": N_GAUSS * world * args.steps / (ms_dev * 1e-3),
-        "op_surface": {"what": "same step through the reference's 7-op surface (calc_J=True) + torch.bmm "
-                               "Jacobian chain (GSFunction mirror of gsmodel.py:6-93)",
+        "op_surface": {"what": "same step through the reference's 7-op surface (calc_J=True) and its Jacobian "
+                               "chain exactly as gsmodel.py:6-93 writes it (GSFunction mirror); the chain's `@` "
+                               "products on our JacobianTensor outputs run on gsb_small_bmm",
                        "value": pix * ops_steps / (ms_ops * 1e-3) / 1e6, "unit": "Mpixels/s",
                        "ms_per_step": ms_ops / ops_steps},
         "grad_max_rel_err_vs_cpu": err["grad_max_rel_err"], "parity_vs_cpu": err,
