@@ -84,19 +84,45 @@ __global__ void __launch_bounds__(256) k_keys(int N, const float *__restrict__ d
                                               const uint2 *__restrict__ rects, int gx, int shift,
                                               KeyT *__restrict__ keys, int32_t *__restrict__ vals) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= N) return;
-  const float d = __ldg(depths + i);
-  if (d < MIN_DEPTH) return;
-  uint32_t off = (i == 0) ? 0u : __ldg(incl + i - 1);
-  const uint2 r = __ldg(rects + i);
-  const uint32_t x0 = r.x & 0xffffu, x1 = r.x >> 16, y0 = r.y & 0xffffu, y1 = r.y >> 16;
-  const KeyT dk = (KeyT)__float2uint_rz(__fmul_rn(d, 1000.0f));
-  for (uint32_t y = y0; y < y1; y++)
-    for (uint32_t x = x0; x < x1; x++) {
-      keys[off] = ((KeyT)(y * (uint32_t)gx + x) << shift) | dk;
-      vals[off] = i;
-      off++;
+  const int lane = threadIdx.x & 31;
+  uint32_t off = 0, x0 = 0, x1 = 0, y0 = 0, y1 = 0;
+  KeyT dk = 0;
+  if (i < N) {
+    const float d = __ldg(depths + i);
+    if (!(d < MIN_DEPTH)) {
+      off = (i == 0) ? 0u : __ldg(incl + i - 1);
+      const uint2 r = __ldg(rects + i);
+      x0 = r.x & 0xffffu; x1 = r.x >> 16; y0 = r.y & 0xffffu; y1 = r.y >> 16;
+      dk = (KeyT)__float2uint_rz(__fmul_rn(d, 1000.0f));
     }
+  }
+  const uint32_t w = x1 - x0, n = w * (y1 - y0);
+  // small rectangles: the owning lane emits them; large ones (a Gaussian covering dozens or
+  // hundreds of tiles) are emitted by the whole warp, 32 patches per step, so one huge
+  // footprint does not serialise its warp
+  if (n <= 32) {
+    for (uint32_t y = y0; y < y1; y++)
+      for (uint32_t x = x0; x < x1; x++) {
+        keys[off] = ((KeyT)(y * (uint32_t)gx + x) << shift) | dk;
+        vals[off] = i;
+        off++;
+      }
+  }
+  unsigned big = __ballot_sync(0xffffffffu, n > 32);
+  while (big) {
+    const int src = __ffs(big) - 1;
+    big &= big - 1;
+    const uint32_t bn = __shfl_sync(0xffffffffu, n, src), bw = __shfl_sync(0xffffffffu, w, src);
+    const uint32_t bx0 = __shfl_sync(0xffffffffu, x0, src), by0 = __shfl_sync(0xffffffffu, y0, src);
+    const uint32_t boff = __shfl_sync(0xffffffffu, off, src);
+    const KeyT bdk = (KeyT)__shfl_sync(0xffffffffu, (unsigned long long)dk, src);
+    const int bi = __shfl_sync(0xffffffffu, i, src);
+    for (uint32_t t = lane; t < bn; t += 32) {  // row-major inside the rectangle == reference order
+      const uint32_t y = by0 + t / bw, x = bx0 + t % bw;
+      keys[boff + t] = ((KeyT)(y * (uint32_t)gx + x) << shift) | bdk;
+      vals[boff + t] = bi;
+    }
+  }
 }
 
 template <typename KeyT>

@@ -246,6 +246,26 @@ def test_splat_alpha_clamp_and_tiny_alpha():
     run_splat_case(N, W, H, sc=sc, seed=2)
 
 
+def test_splat_huge_and_needle_gaussians():
+    """footprints covering hundreds of tiles, extreme anisotropy (needles at 45 degrees) and
+    Gaussians centred far outside the frame whose 3-sigma box still reaches it"""
+    W, H, N = 400, 304, 3000
+    sc = synthetic_scene(N, W, H, sh_dim=3, seed=13)
+    rng = np.random.default_rng(13)
+    big = rng.choice(N, 40, replace=False)
+    sc["scales"][big] *= rng.uniform(20, 60, (40, 1)).astype(np.float32)      # sigma up to ~200 px
+    needle = rng.choice(N, 300, replace=False)
+    sc["scales"][needle, 0] *= 40.0                                            # 100:1 anisotropy
+    sc["scales"][needle, 1:] *= 0.4
+    far = rng.choice(N, 100, replace=False)
+    sc["pws"][far, 0] *= 1.6                                                   # centres off-screen
+    sc["scales"][far] *= 15.0
+    sc["alphas"][big] = rng.uniform(0.02, 0.3, 40).astype(np.float32)
+    _, _, out, ref = run_splat_case(N, W, H, sc=sc, seed=13)
+    lens = ref["ranges"][:, 1] - ref["ranges"][:, 0]
+    assert ref["P"] > 15 * N and lens.min() > 30      # every tile is covered by the big ones
+
+
 def test_splat_golden_blend_fixture():
     """image + splatB grads the reference's backward_cpu.py produced (tests/golden/blend.npz)"""
     bl = dict(np.load(os.path.join(G, "blend.npz")))
