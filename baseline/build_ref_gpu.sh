@@ -1,17 +1,27 @@
 #!/usr/bin/env bash
-# Builds the UNMODIFIED reference `gsplatcu` CUDA extension (gsplatcu/setup.py:4-14 of the
-# reference tree) for sm_100a into baseline/_ref/ so that benchmarks/compare_ref_gpu.py can
-# time it next to ours on the same B200 ("B-REF-GPU" in BASELINE.md).
-# The reference tree is read-only, so the build runs from a scratch copy under /tmp; no
-# reference source enters this repository (baseline/_ref/ is git-ignored, only the built .so
-# lands there).  Only runs where /root/reference exists (the dev container).
+# Installs the UNMODIFIED reference into baseline/_ref/ (git-ignored; it travels to the GPU
+# box with the gpurun snapshot, like a `pip install --target baseline/_ref` would):
+#   baseline/_ref/gsplatcu*.so   the reference's CUDA extension (gsplatcu/setup.py:4-14) built
+#                                for sm_100a -- benchmarks/compare_ref_gpu.py times it next to
+#                                ours on the same B200 ("B-REF-GPU" in BASELINE.md)
+#   baseline/_ref/py/            the reference's pure-Python package gsplat/ and train.py, so
+#                                benchmarks/train_reference.py can run the reference's own
+#                                training script (BASELINE config 3) on either gsplatcu
+# The reference tree is read-only, so the build runs from a scratch copy under /tmp.  No
+# reference source enters this repository's history.  Only runs where /root/reference exists
+# (the dev container).   usage: build_ref_gpu.sh [py]   ("py": only refresh baseline/_ref/py)
 set -euo pipefail
 REF=${REF:-/root/reference}
 OUT="$(cd "$(dirname "$0")" && pwd)/_ref"
 [ -d "$REF/gsplatcu" ] || { echo "no reference tree at $REF - skipping"; exit 0; }
+mkdir -p "$OUT/py"
+rm -rf "$OUT/py/gsplat"
+cp -r "$REF/gsplat" "$OUT/py/gsplat"
+cp "$REF/train.py" "$OUT/py/train.py"
+find "$OUT/py" -name __pycache__ -prune -exec rm -rf {} +
+if [ "${1:-}" = "py" ]; then ls "$OUT" "$OUT/py"; exit 0; fi
 TMP=$(mktemp -d /tmp/refgsplatcu.XXXXXX)
 cp -r "$REF/gsplatcu" "$TMP/src"
-mkdir -p "$OUT"
 cd "$TMP/src"
 TORCH_CUDA_ARCH_LIST="10.0a" MAX_JOBS=4 python setup.py build_ext --build-lib "$OUT" --build-temp "$TMP/build" > "$TMP/build.log" 2>&1 \
   || { tail -30 "$TMP/build.log"; exit 1; }

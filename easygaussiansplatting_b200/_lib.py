@@ -8,6 +8,17 @@ LIB_PATH = os.path.join(_HERE, "libgsplat_b200.so")
 
 _vp, _i, _f, _i64, _sz = C.c_void_p, C.c_int, C.c_float, C.c_int64, C.c_size_t
 
+GAUSSIAN_TENSORS = ("pws", "low_shs", "high_shs", "alphas_raw", "scales_raw", "rots_raw")
+GAUSSIAN_WIDTHS = (3, 3, 45, 1, 3, 4)
+
+
+class Gaussians(C.Structure):
+    """gsb_gaussians: device pointers of the reference's six training tensors"""
+    _fields_ = [(k, _vp) for k in GAUSSIAN_TENSORS]
+
+
+_gp = C.POINTER(Gaussians)
+
 # name -> (restype, argtypes); mirrors include/gsplat_b200.h one to one
 SIGNATURES = {
     "gsb_abi_version": (_i, []),
@@ -31,6 +42,14 @@ SIGNATURES = {
     "gsb_small_bmm": (_i, [C.c_longlong, _i, _i, _i, _vp, _vp, _i, _vp, _vp]),
     "gsb_gau_loss_workspace_bytes": (_sz, [_i, _i]),
     "gsb_gau_loss": (_i, [_i, _i, _vp, _vp, _f, _vp, _vp, _vp, _sz, _vp]),
+    "gsb_density_accumulate": (_i, [_i64, _vp, _vp, _vp, _vp, _i, _vp]),
+    "gsb_density_workspace_bytes": (_sz, [_i64]),
+    "gsb_density_plan": (_i, [_i64, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _vp, _sz, _vp, _vp, C.POINTER(_i64), _vp]),
+    "gsb_density_apply": (_i, [_i64, _vp, _vp, _i64, _i64, _i64, _gp, _gp, _gp, _vp, _gp, _gp, _gp, _vp]),
+    "gsb_reset_alpha": (_i, [_i64, _vp, _vp, _vp, _f, _vp]),
+    "gsb_ply_rows_to_gs": (_i, [_i64, _i, _i, _vp, _vp, _vp, _vp]),
+    "gsb_gs_to_params": (_i, [_i64, _i, _vp, _gp, _vp]),
+    "gsb_params_to_gs": (_i, [_i64, _gp, _vp, _vp]),
     "gsb_set_option": (_i, [C.c_char_p, _i]),
     "gsb_profile_enable": (None, [_i]),
     "gsb_profile_kernels": (_i, []),

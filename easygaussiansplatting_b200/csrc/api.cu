@@ -45,7 +45,9 @@ static const char *const g_names[K_COUNT] = {"project", "computeCov3D", "compute
                                              "ranges", "pack_records", "draw", "draw_backward",
                                              "preprocess_forward", "preprocess_backward",
                                              "finalize_splat_grads", "gau_loss_forward", "gau_loss_backward",
-                                             "small_bmm"};
+                                             "small_bmm", "density_accumulate", "density_classify",
+                                             "density_scan(cub)", "density_apply", "reset_alpha",
+                                             "ply_rows_to_gs", "gs_to_params", "params_to_gs"};
 
 ProfScope::ProfScope(int id, cudaStream_t st) : id_(id), st_(st), stop_(nullptr) {
   std::lock_guard<std::mutex> lk(g_prof_mu);
@@ -323,6 +325,92 @@ int gsb_splat_backward(int H, int W, int N, int64_t P, const float *us, const fl
   return launch_draw_backward(H, W, N, patch_range_per_tile, P > 0 ? recs : nullptr, contrib, final_tau,
                               dloss_dgammas, cinv2ds, moments, tile_counter, dloss_dus, dloss_dcinv2ds,
                               dloss_dalphas, dloss_dcolors, st);
+}
+
+// ---- density control + record conversion (density.cu)
+
+static bool gau_complete(const gsb_gaussians *g) {
+  return g && g->pws && g->low_shs && g->high_shs && g->alphas_raw && g->scales_raw && g->rots_raw;
+}
+static float *const *gau_ptrs(const gsb_gaussians *g) {
+  // six consecutive float* members: the struct IS the pointer table the launchers index
+  static_assert(sizeof(gsb_gaussians) == 6 * sizeof(float *), "gsb_gaussians layout");
+  return reinterpret_cast<float *const *>(g);
+}
+
+int gsb_density_accumulate(int64_t N, const float *dloss_dus, const uint8_t *mask, float *grad_accum,
+                           int32_t *cunt, int first, gsb_stream_t stream) {
+  GSB_REQUIRE(N >= 0, "density_accumulate: N < 0");
+  GSB_REQUIRE(N == 0 || (dloss_dus && mask && grad_accum && cunt), "density_accumulate: null pointer");
+  return launch_density_accumulate(N, dloss_dus, mask, grad_accum, cunt, first, (cudaStream_t)stream);
+}
+
+size_t gsb_density_workspace_bytes(int64_t N) { return density_workspace_bytes(N); }
+
+int gsb_density_plan(int64_t N, const float *alphas_raw, const float *scales_raw, const float *grad_accum,
+                     const int32_t *cunt, float alpha_raw_min, float scale_raw_max, float grad_min,
+                     float scale_clone_max, void *ws, size_t ws_bytes, uint8_t *cls, int32_t *slots,
+                     int64_t *counts_host, gsb_stream_t stream) {
+  GSB_REQUIRE(N >= 0 && N < ((int64_t)1 << 31), "density_plan: N out of range");
+  GSB_REQUIRE(counts_host != nullptr, "density_plan: counts_host is null");
+  GSB_REQUIRE(N == 0 || (alphas_raw && scales_raw && grad_accum && cunt && ws && cls && slots),
+              "density_plan: null pointer");
+  GSB_REQUIRE(N == 0 || ws_bytes >= density_workspace_bytes(N), "density_plan: workspace too small");
+  return launch_density_plan(N, alphas_raw, scales_raw, grad_accum, cunt, alpha_raw_min, scale_raw_max, grad_min,
+                             scale_clone_max, ws, ws_bytes, cls, slots, counts_host, (cudaStream_t)stream);
+}
+
+int gsb_density_apply(int64_t N, const uint8_t *cls, const int32_t *slots, int64_t K, int64_t C, int64_t S,
+                      const gsb_gaussians *src, const gsb_gaussians *src_m, const gsb_gaussians *src_v,
+                      const float *z, const gsb_gaussians *dst, const gsb_gaussians *dst_m,
+                      const gsb_gaussians *dst_v, gsb_stream_t stream) {
+  GSB_REQUIRE(N >= 0 && K >= 0 && C >= 0 && S >= 0 && K <= N && C + S <= K, "density_apply: bad counts");
+  if (N == 0) return 0;
+  GSB_REQUIRE(cls && slots, "density_apply: null plan");
+  GSB_REQUIRE(gau_complete(src), "density_apply: src has a null tensor");
+  GSB_REQUIRE(K + C + S == 0 || gau_complete(dst), "density_apply: dst has a null tensor");
+  const bool state = src_m != nullptr;
+  GSB_REQUIRE((src_v != nullptr) == state && (dst_m != nullptr) == state && (dst_v != nullptr) == state,
+              "density_apply: Adam moments must be all given or all NULL");
+  if (state)
+    GSB_REQUIRE(gau_complete(src_m) && gau_complete(src_v) && (K + C + S == 0 || (gau_complete(dst_m) && gau_complete(dst_v))),
+                "density_apply: a moment tensor is null");
+  GSB_REQUIRE(S == 0 || z != nullptr, "density_apply: z is null");
+  if (K + C + S == 0) return 0;
+  return launch_density_apply(N, cls, slots, K, C, gau_ptrs(src), state ? gau_ptrs(src_m) : nullptr,
+                              state ? gau_ptrs(src_v) : nullptr, z, gau_ptrs(dst), state ? gau_ptrs(dst_m) : nullptr,
+                              state ? gau_ptrs(dst_v) : nullptr, (cudaStream_t)stream);
+}
+
+int gsb_reset_alpha(int64_t N, float *alphas_raw, float *exp_avg, float *exp_avg_sq, float reset_raw,
+                    gsb_stream_t stream) {
+  GSB_REQUIRE(N >= 0, "reset_alpha: N < 0");
+  GSB_REQUIRE(N == 0 || alphas_raw, "reset_alpha: null pointer");
+  return launch_reset_alpha(N, alphas_raw, exp_avg, exp_avg_sq, reset_raw, (cudaStream_t)stream);
+}
+
+static bool sh_dim_ok(int d) { return d == 3 || d == 12 || d == 27 || d == 48; }
+
+int gsb_ply_rows_to_gs(int64_t N, int stride, int sh_dim, const float *rows, const int32_t *colmap,
+                       float *gs_rows, gsb_stream_t stream) {
+  GSB_REQUIRE(N >= 0 && sh_dim_ok(sh_dim), "ply_rows_to_gs: sh_dim must be 3, 12, 27 or 48");
+  GSB_REQUIRE(stride >= 11 + sh_dim, "ply_rows_to_gs: row stride smaller than 11 + sh_dim");
+  GSB_REQUIRE(N == 0 || (rows && colmap && gs_rows), "ply_rows_to_gs: null pointer");
+  return launch_ply_rows_to_gs(N, stride, sh_dim, rows, colmap, gs_rows, (cudaStream_t)stream);
+}
+
+int gsb_gs_to_params(int64_t N, int sh_dim, const float *gs_rows, const gsb_gaussians *dst, gsb_stream_t stream) {
+  GSB_REQUIRE(N >= 0 && sh_dim_ok(sh_dim), "gs_to_params: sh_dim must be 3, 12, 27 or 48");
+  GSB_REQUIRE(N == 0 || (gs_rows && gau_complete(dst)), "gs_to_params: null pointer");
+  if (N == 0) return 0;
+  return launch_gs_to_params(N, sh_dim, gs_rows, gau_ptrs(dst), (cudaStream_t)stream);
+}
+
+int gsb_params_to_gs(int64_t N, const gsb_gaussians *src, float *gs_rows, gsb_stream_t stream) {
+  GSB_REQUIRE(N >= 0, "params_to_gs: N < 0");
+  GSB_REQUIRE(N == 0 || (gs_rows && gau_complete(src)), "params_to_gs: null pointer");
+  if (N == 0) return 0;
+  return launch_params_to_gs(N, gau_ptrs(src), gs_rows, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -1,0 +1,388 @@
+// Density control (prune / clone / split with the Adam moments carried along) and Gaussian
+// record conversion (PLY rows <-> .npy rows <-> the six training tensors).  SURVEY 8f row N3.
+//
+// Reference: gsplat/gsmodel.py:132-166 (update_params / prune_params), :219-234
+// (update_density_info), :236-318 (update_gaussian_density), :320-331 (reset_alpha);
+// gsplat/gau_io.py:60-107 (load_ply), :138-153 (save_training_params); gsmodel.py:95-113
+// (get_training_params).
+//
+// The reference rebuilds all 18 tensors (6 parameters + exp_avg + exp_avg_sq) with boolean
+// indexing and torch.cat, one tensor at a time, plus ~20 temporaries.  Here it is three
+// streaming passes: classify (one byte per Gaussian), one CUB scan over a three-counter
+// struct (the output slot of every survivor / clone / split), and one apply kernel that moves
+// every surviving row once and writes the new rows at the tail.  All of it is HBM-bound:
+// algorithmic bytes = 24 N (classify + scan) + 2 * 708 * K + 708 * (C + S) for the full state
+// (59 floats x 3 sets = 708 B per Gaussian).
+//
+// Transcendentals are the accurate expf / logf / sqrtf / IEEE division (no fast-math here):
+// torch's CUDA kernels use the same libdevice routines, which keeps the clone / split values
+// within an ulp of the reference's.
+#include <cub/device/device_scan.cuh>
+#include <cub/iterator/transform_input_iterator.cuh>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace gsb {
+
+namespace {
+
+constexpr int kWidth[6] = {3, 3, 45, 1, 3, 4};  // pws, low_shs, high_shs, alphas_raw, scales_raw, rots_raw
+enum : uint8_t { CLS_KEEP = 0, CLS_CLONE = 1, CLS_SPLIT = 2, CLS_PRUNE = 3 };
+
+struct Slot3 {  // exclusive counts of survivors / clones / splits before this Gaussian
+  int k, c, s;
+};
+struct SlotAdd {
+  __host__ __device__ Slot3 operator()(const Slot3 &a, const Slot3 &b) const {
+    return Slot3{a.k + b.k, a.c + b.c, a.s + b.s};
+  }
+};
+struct ClsToSlot {
+  __host__ __device__ Slot3 operator()(uint8_t c) const {
+    return Slot3{c != CLS_PRUNE, c == CLS_CLONE, c == CLS_SPLIT};
+  }
+};
+
+// gsmodel.py:219-234.  init != 0 is the first call after a density update: the norm of every
+// Gaussian is stored and the counter starts from the mask (:228-229).
+__global__ void k_density_accumulate(int64_t N, const float2 *__restrict__ dus, const uint8_t *__restrict__ mask,
+                                     float *__restrict__ acc, int32_t *__restrict__ cnt, int init) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const float2 d = dus[i];
+  const float g = sqrtf(d.x * d.x + d.y * d.y);
+  const bool m = mask[i] != 0;
+  if (init) {
+    acc[i] = g;
+    cnt[i] = m;
+  } else if (m) {
+    acc[i] += g;
+    cnt[i] += 1;
+  }
+}
+
+// gsmodel.py:238-262
+__global__ void k_density_classify(int64_t N, const float *__restrict__ alphas_raw,
+                                   const float *__restrict__ scales_raw, const float *__restrict__ acc,
+                                   const int32_t *__restrict__ cnt, float alpha_raw_min, float scale_raw_max,
+                                   float grad_min, float scale_clone_max, uint8_t *__restrict__ cls) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const float a = alphas_raw[i];
+  const float s0 = scales_raw[3 * i], s1 = scales_raw[3 * i + 1], s2 = scales_raw[3 * i + 2];
+  const float smax = fmaxf(s0, fmaxf(s1, s2));
+  uint8_t c;
+  if (a < alpha_raw_min || smax > scale_raw_max) {
+    c = CLS_PRUNE;
+  } else {
+    float g = acc[i] / (float)cnt[i];
+    if (isnan(g)) g = 0.f;
+    // max over exp(s) (the reference compares the activated scales, :257)
+    const float big = fmaxf(expf(s0), fmaxf(expf(s1), expf(s2)));
+    c = g >= grad_min ? (big <= scale_clone_max ? CLS_CLONE : CLS_SPLIT) : CLS_KEEP;
+  }
+  cls[i] = c;
+}
+
+__global__ void k_density_totals(int64_t N, const uint8_t *__restrict__ cls, const Slot3 *__restrict__ slots,
+                                 int64_t *__restrict__ totals) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    Slot3 t = slots[N - 1];
+    const Slot3 l = ClsToSlot()(cls[N - 1]);
+    totals[0] = t.k + l.k;
+    totals[1] = t.c + l.c;
+    totals[2] = t.s + l.s;
+  }
+}
+
+struct Sets {
+  const float *p[6], *m[6], *v[6];  // m / v entries may be null (no optimizer state yet)
+  float *dp[6], *dm[6], *dv[6];
+};
+
+__device__ __forceinline__ float logit_of_sigmoid(float x) {
+  const float a = 1.f / (1.f + expf(-x));  // get_alphas
+  return logf(a / (1.f - a));              // get_alphas_raw
+}
+
+// utils.py:46-54 on the normalised quaternion, v = z * exp(scales_raw)
+__device__ __forceinline__ float split_offset(const float *__restrict__ q4, const float *__restrict__ s3,
+                                              const float *__restrict__ z3, int comp) {
+  float w = q4[0], x = q4[1], y = q4[2], z = q4[3];
+  float n = fmaxf(sqrtf(w * w + x * x + y * y + z * z), 1e-12f);  // get_rots
+  w /= n, x /= n, y /= n, z /= n;
+  n = fmaxf(sqrtf(w * w + x * x + y * y + z * z), 1e-12f);        // normalize() inside rotate_vector
+  w /= n, x /= n, y /= n, z /= n;
+  const float v0 = z3[0] * expf(s3[0]), v1 = z3[1] * expf(s3[1]), v2 = z3[2] * expf(s3[2]);
+  const float uv = x * v0 + y * v1 + z * v2, uu = x * x + y * y + z * z;
+  const float c0 = y * v2 - z * v1, c1 = z * v0 - x * v2, c2 = x * v1 - y * v0;
+  const float u = comp == 0 ? x : (comp == 1 ? y : z);
+  const float v = comp == 0 ? v0 : (comp == 1 ? v1 : v2);
+  const float c = comp == 0 ? c0 : (comp == 1 ? c1 : c2);
+  return 2.f * u * uv + v * (w * w - uu) + 2.f * c * w;
+}
+
+// One element of one of the six tensors per thread (blockIdx.y = tensor, grid-stride over
+// its N*w elements): survivors move to their compacted row, clones / splits additionally
+// produce a new row at K + slot (clones) or K + C + slot (splits) with zero Adam moments.
+template <int A>
+__device__ __forceinline__ void apply_tensor(int64_t N, const uint8_t *__restrict__ cls,
+                                             const Slot3 *__restrict__ slots, int64_t K, int64_t C,
+                                             const Sets &S, const float *__restrict__ z) {
+  constexpr int w = kWidth[A];
+  const float *__restrict__ src = S.p[A];
+  const float *__restrict__ sm = S.m[A];
+  const float *__restrict__ sv = S.v[A];
+  float *__restrict__ dst = S.dp[A];
+  float *__restrict__ dm = S.dm[A];
+  float *__restrict__ dv = S.dv[A];
+  const int64_t total = N * w;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = e / w;
+    const int c = (int)(e - i * w);
+    const uint8_t cl = cls[i];
+    if (cl == CLS_PRUNE) continue;
+    const Slot3 sl = slots[i];
+    const float val = src[e];
+    const int64_t o = (int64_t)sl.k * w + c;
+    dst[o] = val;
+    if (sm) dm[o] = sm[e];
+    if (sv) dv[o] = sv[e];
+    if (cl == CLS_KEEP) continue;
+    const bool split = cl == CLS_SPLIT;
+    const int64_t r = (split ? K + C + sl.s : K + sl.c) * w + c;
+    float nv = val;
+    if (A == 0) {
+      if (split) nv = val + split_offset(S.p[5] + 4 * i, S.p[4] + 3 * i, z + 3 * (int64_t)sl.s, c);
+    } else if (A == 3) {
+      nv = logit_of_sigmoid(val);
+    } else if (A == 4) {
+      const float s = expf(val);               // get_scales
+      nv = logf(split ? s * 0.6f : s);         // gsmodel.py:281 then get_scales_raw
+    } else if (A == 5) {
+      const float *q = src + 4 * i;
+      nv = val / fmaxf(sqrtf(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]), 1e-12f);
+    }
+    dst[r] = nv;
+    if (dm) dm[r] = 0.f;
+    if (dv) dv[r] = 0.f;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_density_apply(int64_t N, const uint8_t *__restrict__ cls,
+                                                       const Slot3 *__restrict__ slots, int64_t K, int64_t C,
+                                                       Sets S, const float *__restrict__ z) {
+  switch (blockIdx.y) {
+    case 0: apply_tensor<0>(N, cls, slots, K, C, S, z); break;
+    case 1: apply_tensor<1>(N, cls, slots, K, C, S, z); break;
+    case 2: apply_tensor<2>(N, cls, slots, K, C, S, z); break;
+    case 3: apply_tensor<3>(N, cls, slots, K, C, S, z); break;
+    case 4: apply_tensor<4>(N, cls, slots, K, C, S, z); break;
+    default: apply_tensor<5>(N, cls, slots, K, C, S, z); break;
+  }
+}
+
+// gsmodel.py:320-331
+__global__ void k_reset_alpha(int64_t N, float *__restrict__ alphas_raw, float *__restrict__ m,
+                              float *__restrict__ v, float val) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  if (alphas_raw[i] > val) alphas_raw[i] = val;
+  if (m) m[i] = 0.f;
+  if (v) v[i] = 0.f;
+}
+
+// ---- record conversion.  A "gs row" is the reference's .npy record (gau_io.py:7-12):
+// pw[3] rot[4] scale[3] alpha sh[sh_dim], 11 + sh_dim floats, activated values.
+
+// gau_io.py:60-107.  rows: the PLY vertex block [N, stride] f32; colmap[j] = source column of
+// output column j (the f_rest channel-major -> coefficient-major transpose of :91 is folded
+// into the map by the host).  rot is divided by its norm (no epsilon, :80), scale -> exp,
+// opacity -> sigmoid.
+__global__ void k_ply_rows_to_gs(int64_t N, int stride, int J, const float *__restrict__ rows,
+                                 const int32_t *__restrict__ colmap, float *__restrict__ out) {
+  const int64_t total = N * J;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = e / J;
+    const int j = (int)(e - i * J);
+    const float *__restrict__ row = rows + i * stride;
+    float v = row[colmap[j]];
+    if (j >= 3 && j < 7) {
+      const float a = row[colmap[3]], b = row[colmap[4]], c = row[colmap[5]], d = row[colmap[6]];
+      v = v / sqrtf(a * a + b * b + c * c + d * d);
+    } else if (j >= 7 && j < 10) {
+      v = expf(v);
+    } else if (j == 10) {
+      v = 1.f / (1.f + expf(-v));
+    }
+    out[e] = v;
+  }
+}
+
+// gsmodel.py:95-113: gs rows -> raw training tensors; high_shs padded with 0.001 up to 45
+__global__ void k_gs_to_params(int64_t N, int sh_dim, const float *__restrict__ gs, float *__restrict__ pws,
+                               float *__restrict__ low, float *__restrict__ high, float *__restrict__ alphas_raw,
+                               float *__restrict__ scales_raw, float *__restrict__ rots_raw) {
+  const int J = 11 + sh_dim;
+  const int64_t total = N * 59;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = e / 59;
+    const int c = (int)(e - i * 59);
+    const float *__restrict__ row = gs + i * J;
+    if (c < 3) {
+      pws[3 * i + c] = row[c];
+    } else if (c < 7) {
+      rots_raw[4 * i + c - 3] = row[c];
+    } else if (c < 10) {
+      scales_raw[3 * i + c - 7] = logf(row[c]);
+    } else if (c == 10) {
+      const float a = row[10];
+      alphas_raw[i] = logf(a / (1.f - a));
+    } else if (c < 14) {
+      low[3 * i + c - 11] = row[c];
+    } else {
+      const int h = c - 14;
+      high[45 * i + h] = (h + 3 < sh_dim) ? row[c] : 0.001f;
+    }
+  }
+}
+
+// gau_io.py:138-153: training tensors -> gs rows with sh_dim = 48
+__global__ void k_params_to_gs(int64_t N, const float *__restrict__ pws, const float *__restrict__ low,
+                               const float *__restrict__ high, const float *__restrict__ alphas_raw,
+                               const float *__restrict__ scales_raw, const float *__restrict__ rots_raw,
+                               float *__restrict__ gs) {
+  const int64_t total = N * 59;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = e / 59;
+    const int c = (int)(e - i * 59);
+    float v;
+    if (c < 3) {
+      v = pws[3 * i + c];
+    } else if (c < 7) {
+      const float *q = rots_raw + 4 * i;
+      v = q[c - 3] / fmaxf(sqrtf(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]), 1e-12f);
+    } else if (c < 10) {
+      v = expf(scales_raw[3 * i + c - 7]);
+    } else if (c == 10) {
+      v = 1.f / (1.f + expf(-alphas_raw[i]));
+    } else if (c < 14) {
+      v = low[3 * i + c - 11];
+    } else {
+      v = high[45 * i + c - 14];
+    }
+    gs[e] = v;
+  }
+}
+
+inline int stream_grid(int64_t total, int block) {
+  int64_t b = (total + block - 1) / block;
+  const int64_t cap = 148 * 16;  // grid-stride: a few waves of the 148 SMs
+  return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+}  // namespace
+
+size_t density_workspace_bytes(int64_t N) {
+  size_t tmp = 0;
+  cub::TransformInputIterator<Slot3, ClsToSlot, const uint8_t *> it(nullptr, ClsToSlot());
+  cub::DeviceScan::ExclusiveScan(nullptr, tmp, it, (Slot3 *)nullptr, SlotAdd(), Slot3{0, 0, 0}, (int)(N > 0 ? N : 1));
+  return 256 + tmp;  // [three int64 totals, padded to 256 B][scan temp]
+}
+
+int launch_density_accumulate(int64_t N, const float *dloss_dus, const uint8_t *mask, float *grad_accum,
+                              int32_t *cunt, int init, cudaStream_t st) {
+  if (N == 0) return 0;
+  ProfScope ps(K_DENSITY_ACC, st);
+  k_density_accumulate<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(N, reinterpret_cast<const float2 *>(dloss_dus),
+                                                                     mask, grad_accum, cunt, init);
+  GSB_CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int launch_density_plan(int64_t N, const float *alphas_raw, const float *scales_raw, const float *grad_accum,
+                        const int32_t *cunt, float alpha_raw_min, float scale_raw_max, float grad_min,
+                        float scale_clone_max, void *ws, size_t ws_bytes, uint8_t *cls, int32_t *slots,
+                        int64_t *counts_host, cudaStream_t st) {
+  counts_host[0] = counts_host[1] = counts_host[2] = 0;
+  if (N == 0) return 0;
+  {
+    ProfScope ps(K_DENSITY_CLASSIFY, st);
+    k_density_classify<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(N, alphas_raw, scales_raw, grad_accum, cunt,
+                                                                     alpha_raw_min, scale_raw_max, grad_min,
+                                                                     scale_clone_max, cls);
+    GSB_CUDA_TRY(cudaGetLastError());
+  }
+  int64_t *totals = static_cast<int64_t *>(ws);
+  void *scan_tmp = static_cast<char *>(ws) + 256;
+  size_t tmp = ws_bytes - 256;
+  {
+    ProfScope ps(K_DENSITY_SCAN, st);
+    cub::TransformInputIterator<Slot3, ClsToSlot, const uint8_t *> it(cls, ClsToSlot());
+    GSB_CUDA_TRY(cub::DeviceScan::ExclusiveScan(scan_tmp, tmp, it, reinterpret_cast<Slot3 *>(slots), SlotAdd(),
+                                               Slot3{0, 0, 0}, (int)N, st));
+    k_density_totals<<<1, 32, 0, st>>>(N, cls, reinterpret_cast<const Slot3 *>(slots), totals);
+    GSB_CUDA_TRY(cudaGetLastError());
+  }
+  GSB_CUDA_TRY(cudaMemcpyAsync(counts_host, totals, 3 * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  GSB_CUDA_TRY(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int launch_density_apply(int64_t N, const uint8_t *cls, const int32_t *slots, int64_t K, int64_t C,
+                         float *const *src, float *const *src_m, float *const *src_v, const float *z,
+                         float *const *dst, float *const *dst_m, float *const *dst_v, cudaStream_t st) {
+  if (N == 0) return 0;
+  Sets S;
+  for (int a = 0; a < 6; a++) {
+    S.p[a] = src[a];
+    S.m[a] = src_m ? src_m[a] : nullptr;
+    S.v[a] = src_v ? src_v[a] : nullptr;
+    S.dp[a] = dst[a];
+    S.dm[a] = dst_m ? dst_m[a] : nullptr;
+    S.dv[a] = dst_v ? dst_v[a] : nullptr;
+  }
+  ProfScope ps(K_DENSITY_APPLY, st);
+  dim3 grid(stream_grid(N * 45, 256), 6);
+  k_density_apply<<<grid, 256, 0, st>>>(N, cls, reinterpret_cast<const Slot3 *>(slots), K, C, S, z);
+  GSB_CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int launch_reset_alpha(int64_t N, float *alphas_raw, float *m, float *v, float val, cudaStream_t st) {
+  if (N == 0) return 0;
+  ProfScope ps(K_RESET_ALPHA, st);
+  k_reset_alpha<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(N, alphas_raw, m, v, val);
+  GSB_CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int launch_ply_rows_to_gs(int64_t N, int stride, int sh_dim, const float *rows, const int32_t *colmap, float *gs,
+                          cudaStream_t st) {
+  if (N == 0) return 0;
+  ProfScope ps(K_GS_DECODE, st);
+  const int J = 11 + sh_dim;
+  k_ply_rows_to_gs<<<stream_grid(N * J, 256), 256, 0, st>>>(N, stride, J, rows, colmap, gs);
+  GSB_CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int launch_gs_to_params(int64_t N, int sh_dim, const float *gs, float *const *dst, cudaStream_t st) {
+  if (N == 0) return 0;
+  ProfScope ps(K_GS_TO_PARAMS, st);
+  k_gs_to_params<<<stream_grid(N * 59, 256), 256, 0, st>>>(N, sh_dim, gs, dst[0], dst[1], dst[2], dst[3], dst[4],
+                                                          dst[5]);
+  GSB_CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int launch_params_to_gs(int64_t N, float *const *src, float *gs, cudaStream_t st) {
+  if (N == 0) return 0;
+  ProfScope ps(K_PARAMS_TO_GS, st);
+  k_params_to_gs<<<stream_grid(N * 59, 256), 256, 0, st>>>(N, src[0], src[1], src[2], src[3], src[4], src[5], gs);
+  GSB_CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace gsb

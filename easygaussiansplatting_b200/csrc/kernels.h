@@ -13,7 +13,9 @@ struct Rec;
 // gsb_profile_enable(1) is in effect (bench.py's roofline leg).
 enum KernelId {
   K_PROJECT = 0, K_COV3D, K_COV2D, K_SH2COLOR, K_INVCOV, K_RECTS, K_SCAN, K_KEYS, K_SORT, K_RANGES,
-  K_PACK, K_DRAW, K_DRAW_BWD, K_PRE_FWD, K_PRE_BWD, K_FINALIZE, K_LOSS_FWD, K_LOSS_BWD, K_BMM, K_COUNT
+  K_PACK, K_DRAW, K_DRAW_BWD, K_PRE_FWD, K_PRE_BWD, K_FINALIZE, K_LOSS_FWD, K_LOSS_BWD, K_BMM,
+  K_DENSITY_ACC, K_DENSITY_CLASSIFY, K_DENSITY_SCAN, K_DENSITY_APPLY, K_RESET_ALPHA, K_GS_DECODE,
+  K_GS_TO_PARAMS, K_PARAMS_TO_GS, K_COUNT
 };
 struct ProfScope {
   ProfScope(int id, cudaStream_t st);
@@ -55,6 +57,24 @@ int launch_small_bmm(long long batch, int M, int K, int NN, const float *A, cons
 size_t gau_loss_workspace_bytes(int H, int W);
 int launch_gau_loss(int H, int W, const float *img, const float *gt, float lambda, float *loss_out,
                     float *grad, void *ws, cudaStream_t st);
+
+// ---- density control + Gaussian record conversion (density.cu).  Tensor order everywhere:
+// pws, low_shs, high_shs, alphas_raw, scales_raw, rots_raw (widths 3, 3, 45, 1, 3, 4).
+size_t density_workspace_bytes(int64_t N);
+int launch_density_accumulate(int64_t N, const float *dloss_dus, const uint8_t *mask, float *grad_accum,
+                              int32_t *cunt, int init, cudaStream_t st);
+int launch_density_plan(int64_t N, const float *alphas_raw, const float *scales_raw, const float *grad_accum,
+                        const int32_t *cunt, float alpha_raw_min, float scale_raw_max, float grad_min,
+                        float scale_clone_max, void *ws, size_t ws_bytes, uint8_t *cls, int32_t *slots,
+                        int64_t *counts_host, cudaStream_t st);
+int launch_density_apply(int64_t N, const uint8_t *cls, const int32_t *slots, int64_t K, int64_t C,
+                         float *const *src, float *const *src_m, float *const *src_v, const float *z,
+                         float *const *dst, float *const *dst_m, float *const *dst_v, cudaStream_t st);
+int launch_reset_alpha(int64_t N, float *alphas_raw, float *m, float *v, float val, cudaStream_t st);
+int launch_ply_rows_to_gs(int64_t N, int stride, int sh_dim, const float *rows, const int32_t *colmap, float *gs,
+                          cudaStream_t st);
+int launch_gs_to_params(int64_t N, int sh_dim, const float *gs, float *const *dst, cudaStream_t st);
+int launch_params_to_gs(int64_t N, float *const *src, float *gs, cudaStream_t st);
 
 // ---- binning (binning.cu)
 struct BinLayout {  // carve-up of the phase-1 workspace

@@ -159,6 +159,75 @@ size_t gsb_gau_loss_workspace_bytes(int H, int W);
 int gsb_gau_loss(int H, int W, const float *image, const float *gt_image, float loss_lambda, float *loss_out,
                  float *dloss_dimage, void *ws, size_t ws_bytes, gsb_stream_t stream);
 
+/* ---- density control (extension).  Replaces GSModel.update_density_info,
+ * update_gaussian_density and reset_alpha with prune_params / update_params
+ * (gsplat/gsmodel.py:132-166, 219-331): one classify pass, one scan, one pass that moves every
+ * surviving row of the 6 parameter tensors and their Adam moments exactly once and appends the
+ * clones and splits, instead of 18 boolean-index + torch.cat rebuilds.
+ *
+ * gsb_gaussians: the reference's six training tensors (gsmodel.py:114-127), device pointers
+ * to dense row-major f32.  For the Adam moments pass two more of these (exp_avg, exp_avg_sq);
+ * a NULL struct pointer means "the optimizer has no state yet" (update_params' else branch). */
+typedef struct gsb_gaussians {
+  float *pws;        /* [N,3]  */
+  float *low_shs;    /* [N,3]  */
+  float *high_shs;   /* [N,45] */
+  float *alphas_raw; /* [N,1]  logit of opacity */
+  float *scales_raw; /* [N,3]  log of scale     */
+  float *rots_raw;   /* [N,4]  (w,x,y,z), un-normalised */
+} gsb_gaussians;
+
+/* update_density_info (:219-234): grad_accum[i] += |dloss_dus[i]|, cunt[i] += 1 where mask[i]
+ * (uint8 0/1).  first != 0 reproduces the first call after a density update: grad_accum is
+ * overwritten with the norm of EVERY Gaussian and cunt with the mask (:228-229). */
+int gsb_density_accumulate(int64_t N, const float *dloss_dus, const uint8_t *mask, float *grad_accum,
+                           int32_t *cunt, int first, gsb_stream_t stream);
+
+/* Classification + output slots (:238-262).  Class per Gaussian into cls[N] (0 keep, 1 keep +
+ * clone, 2 keep + split, 3 prune): prune if alphas_raw < alpha_raw_min or max(scales_raw) >
+ * scale_raw_max; else g = grad_accum / cunt (0/0 -> 0); g >= grad_min selects it, and
+ * max(exp(scales_raw)) <= scale_clone_max decides clone vs split.  slots[N,3] int32 = the
+ * exclusive counts of survivors / clones / splits before each Gaussian.
+ * counts_host[3] <- (K survivors, C clones, S splits).  HOST SYNCHRONISATION: waits for the
+ * counts, like the reference's int(torch.sum(...)) reads -- the caller sizes the outputs
+ * (K + C + S rows) and draws the S x 3 unit normals from them. */
+size_t gsb_density_workspace_bytes(int64_t N);
+int gsb_density_plan(int64_t N, const float *alphas_raw, const float *scales_raw, const float *grad_accum,
+                     const int32_t *cunt, float alpha_raw_min, float scale_raw_max, float grad_min,
+                     float scale_clone_max, void *ws, size_t ws_bytes, uint8_t *cls, int32_t *slots,
+                     int64_t *counts_host, gsb_stream_t stream);
+
+/* The rebuild (:236-318 + :132-166).  dst rows: survivors in order, then clones, then splits.
+ * A clone row is (pws, shs, logit(sigmoid(alphas_raw)), log(exp(scales_raw)),
+ * normalize(rots_raw)); a split row moves pws by R(q) (z * exp(scales_raw)) with z[S,3] the
+ * caller's unit normals (the reference draws torch.normal(0, std=scales) = z * std, :276-277)
+ * and shrinks the NEW Gaussian's scale by 0.6 (the original keeps its size, :281-282).  New
+ * rows get zero Adam moments.  src_m/src_v/dst_m/dst_v: NULL, or all four set. */
+int gsb_density_apply(int64_t N, const uint8_t *cls, const int32_t *slots, int64_t K, int64_t C, int64_t S,
+                      const gsb_gaussians *src, const gsb_gaussians *src_m, const gsb_gaussians *src_v,
+                      const float *z, const gsb_gaussians *dst, const gsb_gaussians *dst_m,
+                      const gsb_gaussians *dst_v, gsb_stream_t stream);
+
+/* reset_alpha (:320-331): alphas_raw = min(alphas_raw, reset_raw); the alpha group's Adam
+ * moments (nullable) are zeroed. */
+int gsb_reset_alpha(int64_t N, float *alphas_raw, float *exp_avg, float *exp_avg_sq, float reset_raw,
+                    gsb_stream_t stream);
+
+/* ---- Gaussian record conversion (extension; SURVEY 8f row N3, gsplat/gau_io.py).  A "gs row"
+ * is the reference's .npy record (gau_io.py:7-12): pw[3] rot[4] scale[3] alpha sh[sh_dim],
+ * 11 + sh_dim floats, activated values.
+ * gsb_ply_rows_to_gs: load_ply's arithmetic (:60-107) on the PLY vertex block rows[N,stride]:
+ *   colmap[11 + sh_dim] (device, int32) = source column of each output column (the host folds
+ *   the f_rest channel-major -> coefficient-major transpose of :91 into it); rot / |rot|,
+ *   exp(scale), sigmoid(opacity).
+ * gsb_gs_to_params: get_training_params (gsmodel.py:95-113): gs rows -> the six raw tensors,
+ *   high_shs padded with 0.001 up to 45 columns.   sh_dim in {3, 12, 27, 48}.
+ * gsb_params_to_gs: save_training_params (gau_io.py:138-153): -> gs rows with sh_dim = 48. */
+int gsb_ply_rows_to_gs(int64_t N, int stride, int sh_dim, const float *rows, const int32_t *colmap,
+                       float *gs_rows, gsb_stream_t stream);
+int gsb_gs_to_params(int64_t N, int sh_dim, const float *gs_rows, const gsb_gaussians *dst, gsb_stream_t stream);
+int gsb_params_to_gs(int64_t N, const gsb_gaussians *src, float *gs_rows, gsb_stream_t stream);
+
 /* ---- options.  "raster_variant": 2 (default) = two pixels per lane with packed f32x2
  * arithmetic (FFMA2/FMUL2/FADD2), 1 = one pixel per lane; same results, kept for A/B
  * measurements.  Also read once from the environment variable GSB_RASTER_VARIANT. */
