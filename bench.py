@@ -228,11 +228,14 @@ def run_ours(args, rank, world):
         chk_host.copy_(params["pws"].grad.abs().sum().reshape(1), non_blocking=True)
         main.wait_stream(copy_stream)
 
-    def timed(fn, steps, warmup):
+    def timed(fn, steps, warmup, collective=True):
+        """device time of `steps` calls; collective=True (every rank calls it): barrier on both
+        sides and the max over ranks.  The rank-0-only legs below pass collective=False."""
+        multi = collective and world > 1
         for _ in range(warmup):
             fn()
         torch.cuda.synchronize()
-        if world > 1:
+        if multi:
             dist.barrier()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -242,7 +245,7 @@ def run_ours(args, rank, world):
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
-        if world > 1:
+        if multi:
             dist.barrier()
             tt = torch.tensor([ms], device=dev)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -334,13 +337,57 @@ def run_ours(args, rank, world):
         s12 = F.conv2d(x * gt_img, win, padding=5, groups=3) - mu1 * mu2
         ssim = ((2 * mu1 * mu2 + 1e-4) * (2 * s12 + 9e-4)) / ((mu1.pow(2) + mu2.pow(2) + 1e-4) * (s11 + s22 + 9e-4))
         (0.8 * torch.abs(x - gt_img).mean() + 0.2 * (1 - ssim.mean())).backward()
-    ms_loss_fused = timed(lambda: gau_loss_with_grad(img, gt_img), 10, 3) / 10
-    ms_loss_torch = timed(torch_loss, 5, 2) / 5
+    ms_loss_fused = timed(lambda: gau_loss_with_grad(img, gt_img), 10, 3, collective=False) / 10
+    ms_loss_torch = timed(torch_loss, 5, 2, collective=False) / 5
     loss_bytes = 132 * WH
     loss_info = {"what": "gau_loss forward + dloss/dimage at 1920x1080 (pytorch_ssim.py:64-67 + autograd)",
                  "fused_ms": ms_loss_fused, "torch_chain_ms": ms_loss_torch,
                  "algorithmic_bytes": loss_bytes, "achieved_GBps": loss_bytes / (ms_loss_fused * 1e-3) / 1e9,
                  "hbm_frac": loss_bytes / (ms_loss_fused * 1e-3) / 1e9 / peak}
+
+    # ---- density control (row N3): classify + scan + one-pass rebuild of the 6 parameter
+    # tensors and both Adam moments, on the bench scene's N with a synthetic optimizer state
+    from easygaussiansplatting_b200 import density as dn
+    g = torch.Generator(device=dev).manual_seed(3)
+    widths = dict(zip(dn.GAUSSIAN_TENSORS, dn.GAUSSIAN_WIDTHS))
+    dP = {k: torch.randn((N_GAUSS, w), device=dev, generator=g) for k, w in widths.items()}
+    dP["alphas_raw"] = torch.rand((N_GAUSS, 1), device=dev, generator=g) * 11.5 - 7.5
+    dP["scales_raw"] = torch.log(torch.exp(torch.rand((N_GAUSS, 1), device=dev, generator=g) * 4.1 - 4.6) *
+                                 (torch.rand((N_GAUSS, 3), device=dev, generator=g) * 0.9 + 0.6))
+    dM = {k: torch.randn_like(v) * 1e-3 for k, v in dP.items()}
+    dV = {k: torch.rand_like(v) * 1e-6 for k, v in dP.items()}
+    d_cnt = torch.randint(0, 6, (N_GAUSS,), device=dev, generator=g, dtype=torch.int32)
+    d_acc = torch.randn((N_GAUSS, 1), device=dev, generator=g).abs() * 1.5e-6
+    th = dn.raw_thresholds(5.0)
+    counts = [None]
+
+    def densify_once():
+        cls, slots, cnts = dn.plan(dP["alphas_raw"], dP["scales_raw"], d_acc, d_cnt, th)
+        z = torch.empty((cnts[2], 3), device=dev).normal_()
+        dn.apply(cls, slots, cnts, dP, dM, dV, z)
+        counts[0] = cnts
+    ms_dens = timed(densify_once, 5, 2, collective=False) / 5
+    lib.gsb_profile_enable(1)
+    for _ in range(3):
+        densify_once()
+    torch.cuda.synchronize()
+    lib.gsb_profile_enable(0)
+    dkern = {}
+    for i in range(lib.gsb_profile_kernels()):
+        ms_tot, cnt = C.c_double(0), C.c_longlong(0)
+        lib.gsb_profile_read(i, C.byref(ms_tot), C.byref(cnt))
+        if cnt.value:
+            dkern[lib.gsb_profile_kernel_name(i).decode()] = ms_tot.value / 3
+    Kk, Cc, Ss = counts[0]
+    apply_bytes = 2 * 708 * Kk + 708 * (Cc + Ss) + 13 * N_GAUSS + 12 * Ss   # rows moved once + cls/slots + z
+    dens_info = {"what": "update_gaussian_density on 1M Gaussians with Adam moments (gsmodel.py:132-166, 236-318): "
+                         "gsb_density_plan + gsb_density_apply, incl. the count read-back and output allocation",
+                 "ms": ms_dens, "kernels_ms": dkern, "survivors_clones_splits": [Kk, Cc, Ss],
+                 "apply_algorithmic_bytes": apply_bytes,
+                 "apply_achieved_GBps": apply_bytes / (dkern.get("density_apply", float("nan")) * 1e-3) / 1e9,
+                 "apply_hbm_frac": apply_bytes / (dkern.get("density_apply", float("nan")) * 1e-3) / 1e9 / peak,
+                 "vs_reference": "profiles/r1_compare_density_ref.json (same inputs through the reference's gsmodel.py)"}
+    del dP, dM, dV
 
     # ---- CPU baseline + gradient error vs the CPU oracle on the same crop
     cpu_mpix, cpu_sec, cpu_threads, cpu = cpu_sample(steps=1, warmup=0)
@@ -367,6 +414,7 @@ def run_ours(args, rank, world):
         "roofline": roofline,
         "kernel_ms_per_step": kern,
         "loss_n2": loss_info,
+        "density_n3": dens_info,
         "cpu_baseline": {"value": cpu_mpix, "unit": "Mpixels/s", "cores": cpu_threads, "kind": "port",
                          "sample": sample_text(cpu_sec)},
         "e2e": {"value": e2e, "unit": "Mpixels/s", "ms_per_step": ms_e2e / args.steps,
