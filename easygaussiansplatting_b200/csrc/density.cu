@@ -123,64 +123,80 @@ __device__ __forceinline__ float split_offset(const float *__restrict__ q4, cons
   return 2.f * u * uv + v * (w * w - uu) + 2.f * c * w;
 }
 
-// One element of one of the six tensors per thread (blockIdx.y = tensor, grid-stride over
-// its N*w elements): survivors move to their compacted row, clones / splits additionally
-// produce a new row at K + slot (clones) or K + C + slot (splits) with zero Adam moments.
-template <int A>
-__device__ __forceinline__ void apply_tensor(int64_t N, const uint8_t *__restrict__ cls,
-                                             const Slot3 *__restrict__ slots, int64_t K, int64_t C,
-                                             const Sets &S, const float *__restrict__ z) {
+// One "job" per (tensor, set) pair -- 6 tensors x {parameter, exp_avg, exp_avg_sq} = 18 jobs on
+// blockIdx.y, grid-stride over the job's N*w elements, four independent elements in flight
+// per thread (loads first, then stores).  Survivors move to their compacted row; clones /
+// splits additionally produce a new row at K + slot (clones) or K + C + slot (splits): the
+// recomputed value for a parameter, zero for an Adam moment.  I = int32 whenever every
+// element index fits (N < 23 M), which keeps the divisions by the row width single mul.hi.
+template <int A, int SET, typename I>
+__device__ __forceinline__ void apply_job(I N, const uint8_t *__restrict__ cls, const Slot3 *__restrict__ slots,
+                                          I K, I C, const Sets &S, const float *__restrict__ z) {
   constexpr int w = kWidth[A];
-  const float *__restrict__ src = S.p[A];
-  const float *__restrict__ sm = S.m[A];
-  const float *__restrict__ sv = S.v[A];
-  float *__restrict__ dst = S.dp[A];
-  float *__restrict__ dm = S.dm[A];
-  float *__restrict__ dv = S.dv[A];
-  const int64_t total = N * w;
-  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t i = e / w;
-    const int c = (int)(e - i * w);
-    const uint8_t cl = cls[i];
-    if (cl == CLS_PRUNE) continue;
-    const Slot3 sl = slots[i];
-    const float val = src[e];
-    const int64_t o = (int64_t)sl.k * w + c;
-    dst[o] = val;
-    if (sm) dm[o] = sm[e];
-    if (sv) dv[o] = sv[e];
-    if (cl == CLS_KEEP) continue;
-    const bool split = cl == CLS_SPLIT;
-    const int64_t r = (split ? K + C + sl.s : K + sl.c) * w + c;
-    float nv = val;
-    if (A == 0) {
-      if (split) nv = val + split_offset(S.p[5] + 4 * i, S.p[4] + 3 * i, z + 3 * (int64_t)sl.s, c);
-    } else if (A == 3) {
-      nv = logit_of_sigmoid(val);
-    } else if (A == 4) {
-      const float s = expf(val);               // get_scales
-      nv = logf(split ? s * 0.6f : s);         // gsmodel.py:281 then get_scales_raw
-    } else if (A == 5) {
-      const float *q = src + 4 * i;
-      nv = val / fmaxf(sqrtf(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]), 1e-12f);
+  constexpr int U = 4;
+  const float *__restrict__ src = SET == 0 ? S.p[A] : (SET == 1 ? S.m[A] : S.v[A]);
+  float *__restrict__ dst = SET == 0 ? S.dp[A] : (SET == 1 ? S.dm[A] : S.dv[A]);
+  if (src == nullptr) return;
+  const I total = N * w;
+  const I stride = (I)gridDim.x * blockDim.x;
+  for (I e0 = (I)blockIdx.x * blockDim.x + threadIdx.x; e0 < total; e0 += stride * U) {
+    I row[U];
+    uint8_t cl[U];
+    float val[U];
+    Slot3 sl[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const I e = e0 + (I)u * stride;
+      row[u] = e < total ? e / w : 0;
+      cl[u] = e < total ? cls[row[u]] : (uint8_t)CLS_PRUNE;
     }
-    dst[r] = nv;
-    if (dm) dm[r] = 0.f;
-    if (dv) dv[r] = 0.f;
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      if (cl[u] == CLS_PRUNE) continue;
+      val[u] = src[e0 + (I)u * stride];
+      sl[u] = slots[row[u]];
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      if (cl[u] == CLS_PRUNE) continue;
+      const I i = row[u];
+      const int c = (int)(e0 + (I)u * stride - i * w);
+      dst[(I)sl[u].k * w + c] = val[u];
+      if (cl[u] == CLS_KEEP) continue;
+      const bool split = cl[u] == CLS_SPLIT;
+      const I r = (split ? K + C + (I)sl[u].s : K + (I)sl[u].c) * w + c;
+      float nv = 0.f;
+      if (SET == 0) {
+        nv = val[u];
+        if (A == 0) {
+          if (split) nv += split_offset(S.p[5] + 4 * (int64_t)i, S.p[4] + 3 * (int64_t)i, z + 3 * (int64_t)sl[u].s, c);
+        } else if (A == 3) {
+          nv = logit_of_sigmoid(nv);
+        } else if (A == 4) {
+          const float s = expf(nv);               // get_scales
+          nv = logf(split ? s * 0.6f : s);        // gsmodel.py:281 then get_scales_raw
+        } else if (A == 5) {
+          const float *q = src + 4 * (int64_t)i;
+          nv = nv / fmaxf(sqrtf(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]), 1e-12f);
+        }
+      }
+      dst[r] = nv;
+    }
   }
 }
 
-__global__ void __launch_bounds__(256) k_density_apply(int64_t N, const uint8_t *__restrict__ cls,
-                                                       const Slot3 *__restrict__ slots, int64_t K, int64_t C,
-                                                       Sets S, const float *__restrict__ z) {
+template <typename I>
+__global__ void __launch_bounds__(256) k_density_apply(I N, const uint8_t *__restrict__ cls,
+                                                       const Slot3 *__restrict__ slots, I K, I C, Sets S,
+                                                       const float *__restrict__ z) {
+#define GSB_JOB(a, s) \
+  case 3 * a + s: apply_job<a, s, I>(N, cls, slots, K, C, S, z); break;
   switch (blockIdx.y) {
-    case 0: apply_tensor<0>(N, cls, slots, K, C, S, z); break;
-    case 1: apply_tensor<1>(N, cls, slots, K, C, S, z); break;
-    case 2: apply_tensor<2>(N, cls, slots, K, C, S, z); break;
-    case 3: apply_tensor<3>(N, cls, slots, K, C, S, z); break;
-    case 4: apply_tensor<4>(N, cls, slots, K, C, S, z); break;
-    default: apply_tensor<5>(N, cls, slots, K, C, S, z); break;
+    GSB_JOB(0, 0) GSB_JOB(0, 1) GSB_JOB(0, 2) GSB_JOB(1, 0) GSB_JOB(1, 1) GSB_JOB(1, 2)
+    GSB_JOB(2, 0) GSB_JOB(2, 1) GSB_JOB(2, 2) GSB_JOB(3, 0) GSB_JOB(3, 1) GSB_JOB(3, 2)
+    GSB_JOB(4, 0) GSB_JOB(4, 1) GSB_JOB(4, 2) GSB_JOB(5, 0) GSB_JOB(5, 1) GSB_JOB(5, 2)
   }
+#undef GSB_JOB
 }
 
 // gsmodel.py:320-331
@@ -344,8 +360,12 @@ int launch_density_apply(int64_t N, const uint8_t *cls, const int32_t *slots, in
     S.dv[a] = dst_v ? dst_v[a] : nullptr;
   }
   ProfScope ps(K_DENSITY_APPLY, st);
-  dim3 grid(stream_grid(N * 45, 256), 6);
-  k_density_apply<<<grid, 256, 0, st>>>(N, cls, reinterpret_cast<const Slot3 *>(slots), K, C, S, z);
+  dim3 grid(stream_grid((N * 45 + 3) / 4, 256), 18);
+  if (N < 23000000)
+    k_density_apply<int32_t><<<grid, 256, 0, st>>>((int32_t)N, cls, reinterpret_cast<const Slot3 *>(slots), (int32_t)K,
+                                                   (int32_t)C, S, z);
+  else
+    k_density_apply<int64_t><<<grid, 256, 0, st>>>(N, cls, reinterpret_cast<const Slot3 *>(slots), K, C, S, z);
   GSB_CUDA_TRY(cudaGetLastError());
   return 0;
 }
