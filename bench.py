@@ -183,18 +183,28 @@ def run_ours(args, rank, world):
     img_host = torch.empty((3, HEIGHT, WIDTH), dtype=torch.float32).pin_memory()
     chk_host = torch.empty(1, dtype=torch.float32).pin_memory()
 
-    def make_step(F):
+    # multi-view DP: the parameter gradients are summed over the views.  Product path: the fused
+    # backward pushes its tiles into peer memory + one reduce/broadcast kernel (GradExchange);
+    # the NCCL all-reduce of the same bucket is timed beside it as the library baseline.
+    exchange = None
+    if world > 1:
+        from easygaussiansplatting_b200.parallel import GradExchange
+        exchange = GradExchange.from_process_group(N_GAUSS, SH_DIM // 3, dev)
+
+    def make_step(F, use_exchange):
         def step(dl):
             for p in leaves:
                 p.grad = None
+            cam.grad_exchange = exchange if use_exchange else None
             image, _ = F.apply(params["pws"], params["shs"], alphas, params["scales"], params["rots"], us0, cam)
             image.backward(dl)
-            if world > 1:  # multi-view DP: sum the parameter gradients over the views
+            if world > 1 and not use_exchange:
                 allreduce_grads([p.grad for p in leaves])
             return image
         return step
 
-    step_fused, step_ops = make_step(GSFunctionFused), make_step(GSFunction)
+    step_fused, step_ops = make_step(GSFunctionFused, True), make_step(GSFunction, False)
+    step_fused_nccl = make_step(GSFunctionFused, False)
 
     copy_stream = torch.cuda.Stream(device=dev)
     ev_fwd, ev_dl = torch.cuda.Event(), torch.cuda.Event()
@@ -213,6 +223,7 @@ def run_ours(args, rank, world):
             ev_dl.record(copy_stream)
         for p in leaves:
             p.grad = None
+        cam.grad_exchange = exchange
         image, _ = GSFunctionFused.apply(params["pws"], params["shs"], alphas, params["scales"], params["rots"],
                                          us0, cam)
         ev_fwd.record(main)
@@ -223,8 +234,6 @@ def run_ours(args, rank, world):
             img_host.copy_(img, non_blocking=True)
         main.wait_event(ev_dl)
         image.backward(dl_dev)
-        if world > 1:
-            allreduce_grads([p.grad for p in leaves])
         chk_host.copy_(params["pws"].grad.abs().sum().reshape(1), non_blocking=True)
         main.wait_stream(copy_stream)
 
@@ -272,11 +281,22 @@ def run_ours(args, rank, world):
 
     allreduce = None
     if world > 1:  # the gradient exchange alone (bytes, device time, max over ranks)
-        nbytes = 0
-        ms_ar = timed(lambda: allreduce_grads([p.grad for p in leaves]), 10, 3)
+        # same step with the library collective instead of the fused exchange, and the two
+        # results against each other (the exchange sums in rank order; NCCL's order may differ)
+        step_fused_nccl(dl_dev)
+        ref_grads = [p.grad.clone() for p in leaves]
+        ms_ar = timed(lambda: allreduce_grads([p.grad for p in leaves]), 10, 3)   # grads = flat bucket views
         nbytes = allreduce_grads([p.grad for p in leaves])
+        ms_nccl_step = timed(lambda: step_fused_nccl(dl_dev), max(5, args.steps // 2), 2) / max(5, args.steps // 2)
+        step_fused(dl_dev)
+        torch.cuda.synchronize()
+        diff = max(float((p.grad - g).abs().max() / g.abs().max().clamp_min(1e-30)) for p, g in zip(leaves, ref_grads))
         allreduce = {"bytes": int(nbytes), "ms": ms_ar / 10,
-                     "algbw_GBps": nbytes / (ms_ar / 10 * 1e-3) / 1e9}
+                     "algbw_GBps": nbytes / (ms_ar / 10 * 1e-3) / 1e9,
+                     "what": "NCCL all-reduce of the flat gradient bucket (library baseline); `value` uses the "
+                             "fused push + reduce/broadcast exchange over peer memory instead",
+                     "step_ms_with_nccl_allreduce": ms_nccl_step, "step_ms_with_fused_exchange": ms_dev / args.steps,
+                     "exchange_vs_nccl_max_rel_diff": diff, "exchange_status": exchange.status()}
 
     # ---- per-kernel durations with CUDA events on the launch stream (roofline leg)
     prof_steps = 5

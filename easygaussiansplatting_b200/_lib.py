@@ -50,6 +50,16 @@ SIGNATURES = {
     "gsb_ply_rows_to_gs": (_i, [_i64, _i, _i, _vp, _vp, _vp, _vp]),
     "gsb_gs_to_params": (_i, [_i64, _i, _vp, _gp, _vp]),
     "gsb_params_to_gs": (_i, [_i64, _gp, _vp, _vp]),
+    "gsb_exchange_region_bytes": (_sz, [_i, _i, _i]),
+    "gsb_exchange_result_offset": (_sz, [_i, _i, _i, _i]),
+    "gsb_comm_alloc": (_i, [_sz, C.POINTER(_vp), _vp]),
+    "gsb_comm_open": (_i, [_vp, C.POINTER(_vp)]),
+    "gsb_comm_close": (_i, [_vp]),
+    "gsb_comm_free": (_i, [_vp]),
+    "gsb_exchange_status": (_i, [_vp, C.POINTER(_i)]),
+    "gsb_preprocess_backward_push": (_i, [_i, _i] + [_vp] * 7 + [_f] * 6 + [_vp] * 4 + [_i, _i, C.POINTER(_vp),
+                                                                                          C.c_uint32, _vp]),
+    "gsb_grad_reduce_broadcast": (_i, [_i, _i, _i, _i, C.POINTER(_vp), C.c_uint32, _vp]),
     "gsb_set_option": (_i, [C.c_char_p, _i]),
     "gsb_profile_enable": (None, [_i]),
     "gsb_profile_kernels": (_i, []),

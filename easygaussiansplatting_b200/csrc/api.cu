@@ -47,7 +47,8 @@ static const char *const g_names[K_COUNT] = {"project", "computeCov3D", "compute
                                              "finalize_splat_grads", "gau_loss_forward", "gau_loss_backward",
                                              "small_bmm", "density_accumulate", "density_classify",
                                              "density_scan(cub)", "density_apply", "reset_alpha",
-                                             "ply_rows_to_gs", "gs_to_params", "params_to_gs"};
+                                             "ply_rows_to_gs", "gs_to_params", "params_to_gs",
+                                             "grad_reduce_broadcast"};
 
 ProfScope::ProfScope(int id, cudaStream_t st) : id_(id), st_(st), stop_(nullptr) {
   std::lock_guard<std::mutex> lk(g_prof_mu);
@@ -411,6 +412,101 @@ int gsb_params_to_gs(int64_t N, const gsb_gaussians *src, float *gs_rows, gsb_st
   GSB_REQUIRE(N == 0 || (gs_rows && gau_complete(src)), "params_to_gs: null pointer");
   if (N == 0) return 0;
   return launch_params_to_gs(N, gau_ptrs(src), gs_rows, (cudaStream_t)stream);
+}
+
+// ---- multi-GPU gradient exchange (comm.cu, fused.cu PUSH variant)
+
+size_t gsb_exchange_region_bytes(int N, int sh_dim3, int world) {
+  if (N < 0 || world < 1 || world > kMaxWorld) return 0;
+  return exchange_geom(N, sh_dim3, world).bytes;
+}
+
+size_t gsb_exchange_result_offset(int N, int sh_dim3, int world, int segment) {
+  if (segment < 0 || segment > 4 || world < 1 || world > kMaxWorld) return 0;
+  const ExchangeGeom G = exchange_geom(N, sh_dim3, world);
+  return G.result_base + (size_t)G.result_off[segment] * sizeof(float);
+}
+
+int gsb_comm_alloc(size_t bytes, void **ptr, void *handle_out) {
+  GSB_REQUIRE(ptr && handle_out && bytes > 0, "comm_alloc: bad arguments");
+  static_assert(sizeof(cudaIpcMemHandle_t) == GSB_COMM_HANDLE_BYTES, "IPC handle size");
+  GSB_CUDA_TRY(cudaMalloc(ptr, bytes));
+  GSB_CUDA_TRY(cudaMemset(*ptr, 0, bytes));
+  GSB_CUDA_TRY(cudaDeviceSynchronize());
+  cudaIpcMemHandle_t h;
+  GSB_CUDA_TRY(cudaIpcGetMemHandle(&h, *ptr));
+  memcpy(handle_out, &h, sizeof(h));
+  return 0;
+}
+
+int gsb_comm_open(const void *handle, void **peer_ptr) {
+  GSB_REQUIRE(handle && peer_ptr, "comm_open: bad arguments");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof(h));
+  GSB_CUDA_TRY(cudaIpcOpenMemHandle(peer_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return 0;
+}
+
+int gsb_comm_close(void *peer_ptr) {
+  if (peer_ptr) GSB_CUDA_TRY(cudaIpcCloseMemHandle(peer_ptr));
+  return 0;
+}
+
+int gsb_comm_free(void *ptr) {
+  if (ptr) GSB_CUDA_TRY(cudaFree(ptr));
+  return 0;
+}
+
+int gsb_exchange_status(const void *region, int *status_host) {
+  GSB_REQUIRE(region && status_host, "exchange_status: bad arguments");
+  uint32_t v = 0;
+  GSB_CUDA_TRY(cudaMemcpy(&v, static_cast<const char *>(region) + 136, sizeof(v), cudaMemcpyDeviceToHost));
+  *status_host = (int)v;
+  return 0;
+}
+
+int gsb_preprocess_backward_push(int N, int sh_dim3, const float *pws, const float *rots, const float *scales,
+                                 const float *shs, const float *Rcw, const float *tcw, const float *twc,
+                                 float fx, float fy, float cx, float cy, float width, float height,
+                                 const float *dloss_dus, const float *dloss_dcinv2ds, const float *dloss_dcolors,
+                                 const float *dloss_dalphas, int world, int rank, void *const *regions_host,
+                                 uint32_t epoch, gsb_stream_t stream) {
+  GSB_REQUIRE(N >= 0, "preprocess_backward_push: N < 0");
+  GSB_REQUIRE(world >= 1 && world <= kMaxWorld && rank >= 0 && rank < world && regions_host && epoch != 0,
+              "preprocess_backward_push: bad world / rank / regions / epoch");
+  GSB_REQUIRE(N == 0 || (pws && rots && scales && shs && Rcw && tcw && twc && dloss_dus && dloss_dcinv2ds &&
+                         dloss_dcolors && dloss_dalphas),
+              "preprocess_backward_push: null pointer");
+  const ExchangeGeom G = exchange_geom(N, sh_dim3, world);
+  GradPush gp{};
+  for (int p = 0; p < world; p++) {
+    GSB_REQUIRE(regions_host[p] != nullptr, "preprocess_backward_push: null region");
+    char *r = static_cast<char *>(regions_host[p]);
+    gp.slot[p] = reinterpret_cast<float *>(r + G.staging_off) + (size_t)rank * G.slot_floats;
+    gp.flags[p] = reinterpret_cast<uint32_t *>(r);
+  }
+  gp.counter = reinterpret_cast<uint32_t *>(static_cast<char *>(regions_host[rank]) + 128);
+  gp.g_alphas = dloss_dalphas;
+  gp.rpr = G.rpr;
+  gp.off_rots = G.slot_off[1];
+  gp.off_pws = G.slot_off[2];
+  gp.off_scales = G.slot_off[3];
+  gp.off_alphas = G.slot_off[4];
+  gp.tiles_per_rank = G.tiles_per_rank;
+  gp.world = world;
+  gp.rank = rank;
+  gp.epoch = epoch;
+  return launch_preprocess_bwd_push(N, sh_dim3, pws, rots, scales, shs, Rcw, tcw, twc, fx, fy, cx, cy, width, height,
+                                    dloss_dus, dloss_dcinv2ds, dloss_dcolors, gp, (cudaStream_t)stream);
+}
+
+int gsb_grad_reduce_broadcast(int N, int sh_dim3, int world, int rank, void *const *regions_host, uint32_t epoch,
+                              gsb_stream_t stream) {
+  GSB_REQUIRE(N >= 0 && world >= 1 && world <= kMaxWorld && rank >= 0 && rank < world && regions_host && epoch != 0,
+              "grad_reduce_broadcast: bad arguments");
+  for (int p = 0; p < world; p++) GSB_REQUIRE(regions_host[p] != nullptr, "grad_reduce_broadcast: null region");
+  const ExchangeGeom G = exchange_geom(N, sh_dim3, world);
+  return launch_grad_reduce_bcast(G, rank, regions_host, epoch, (cudaStream_t)stream);
 }
 
 }  // extern "C"

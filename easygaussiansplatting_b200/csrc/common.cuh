@@ -79,6 +79,21 @@ __device__ __forceinline__ bool rec_can_touch(const float4 &q0, const float4 &q1
   return !(qmin > q0.z + fmaf(2.0e-6f, S, 1.0e-5f));  // NaN anywhere keeps the record
 }
 
+// ---- system-scope flags for the multi-GPU gradient exchange (peer memory over NVLink)
+__device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
 // ---- mbarrier + bulk async copy (global -> shared), single-CTA forms
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));

@@ -78,14 +78,20 @@ __global__ void __launch_bounds__(PG) k_preprocess_fwd(
   if (valid) depths[base + tid] = depth;
 }
 
-template <int K3>
+// PUSH = the multi-GPU variant: instead of writing the gradient tile to local
+// buffers, the CTA stores it straight into the staging slot `rank` of the GPU that owns this
+// tile's Gaussians (peer memory over NVLink -- posted stores, so the transfer of tile t
+// overlaps the math of tile t+1), together with dL/dalpha from the rasterizer backward.  The
+// last CTA to finish raises this rank's arrival flag on every peer; k_grad_reduce_bcast
+// (comm.cu) then sums the slots of the rows it owns and broadcasts the result.
+template <int K3, bool PUSH>
 __global__ void __launch_bounds__(PG) k_preprocess_bwd(
     int N, const float *__restrict__ pws, const float *__restrict__ rots, const float *__restrict__ scales,
     const float *__restrict__ shs, const float *__restrict__ Rcw, const float *__restrict__ tcw,
     const float *__restrict__ twc, float fx, float fy, float cx, float cy, float tan_fovx, float tan_fovy,
     const float *__restrict__ g_us, const float *__restrict__ g_cinv2ds, const float *__restrict__ g_colors,
     float *__restrict__ g_pws, float *__restrict__ g_shs, float *__restrict__ g_scales,
-    float *__restrict__ g_rots) {
+    float *__restrict__ g_rots, GradPush gp) {
   constexpr int KS = 3 * K3;
   constexpr int SMF = TileT<KS>::FLOATS > TileT<4>::FLOATS ? TileT<KS>::FLOATS : TileT<4>::FLOATS;
   __shared__ float sm[SMF];
@@ -126,19 +132,42 @@ __global__ void __launch_bounds__(PG) k_preprocess_bwd(
   // dL/dsh overwrites the thread's own SH row in place, then the tile is flushed
   if (valid) pg::backward_one<K3>(pw, q, s, ROWK(KS), cam, gu, gci, gcol, gpw, gq, gs, ROWK(KS));
   __syncthreads();
-  tile_flush<KS>(g_shs, base, nv, sm, tid);
+  long long drow = base;
+  if (PUSH) {  // destination = slot `rank` on the owner of this tile, rows relative to its range
+    const int owner = (int)(blockIdx.x / gp.tiles_per_rank);
+    float *sb = gp.slot[owner];
+    drow = base - (long long)owner * gp.rpr;
+    g_shs = sb;
+    g_rots = sb + gp.off_rots;
+    g_pws = sb + gp.off_pws;
+    g_scales = sb + gp.off_scales;
+    if (valid) (sb + gp.off_alphas)[drow + tid] = __ldg(gp.g_alphas + base + tid);
+  }
+  tile_flush<KS>(g_shs, drow, nv, sm, tid);
   __syncthreads();
   { float *o = ROWK(3); o[0] = gpw[0]; o[1] = gpw[1]; o[2] = gpw[2]; }
   __syncthreads();
-  tile_flush<3>(g_pws, base, nv, sm, tid);
+  tile_flush<3>(g_pws, drow, nv, sm, tid);
   __syncthreads();
   { float *o = ROWK(3); o[0] = gs[0]; o[1] = gs[1]; o[2] = gs[2]; }
   __syncthreads();
-  tile_flush<3>(g_scales, base, nv, sm, tid);
+  tile_flush<3>(g_scales, drow, nv, sm, tid);
   __syncthreads();
   { float *o = ROWK(4); o[0] = gq[0]; o[1] = gq[1]; o[2] = gq[2]; o[3] = gq[3]; }
   __syncthreads();
-  tile_flush<4>(g_rots, base, nv, sm, tid);
+  tile_flush<4>(g_rots, drow, nv, sm, tid);
+  if (PUSH) {
+    __threadfence_system();  // this thread's peer stores are ordered before the flag below
+    __syncthreads();
+    if (tid == 0) {
+      const unsigned done = atomicAdd(gp.counter, 1u);
+      if (done == gridDim.x - 1) {  // last tile of this rank
+        *gp.counter = 0;            // re-armed for the next launch (stream-ordered)
+        __threadfence_system();
+        for (int p = 0; p < gp.world; p++) st_release_sys(gp.flags[p] + gp.rank, gp.epoch);
+      }
+    }
+  }
 }
 
 #define GSB_DISPATCH_K3(k3, CALL)                                           \
@@ -173,9 +202,25 @@ int launch_preprocess_bwd(int N, int k3, const float *pws, const float *rots, co
   const float tfx = width / (2 * fx), tfy = height / (2 * fy);
   const int nb = (N + PG - 1) / PG;
   ProfScope ps(K_PRE_BWD, st);
-  GSB_DISPATCH_K3(k3, (k_preprocess_bwd<K3><<<nb, PG, 0, st>>>(N, pws, rots, scales, shs, Rcw, tcw, twc, fx, fy, cx,
-                                                                cy, tfx, tfy, g_us, g_cinv2ds, g_colors, g_pws,
-                                                                g_shs, g_scales, g_rots)));
+  GSB_DISPATCH_K3(k3, (k_preprocess_bwd<K3, false><<<nb, PG, 0, st>>>(N, pws, rots, scales, shs, Rcw, tcw, twc, fx,
+                                                                       fy, cx, cy, tfx, tfy, g_us, g_cinv2ds,
+                                                                       g_colors, g_pws, g_shs, g_scales, g_rots,
+                                                                       GradPush{})));
+  GSB_CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int launch_preprocess_bwd_push(int N, int k3, const float *pws, const float *rots, const float *scales,
+                               const float *shs, const float *Rcw, const float *tcw, const float *twc, float fx,
+                               float fy, float cx, float cy, float width, float height, const float *g_us,
+                               const float *g_cinv2ds, const float *g_colors, const GradPush &gp, cudaStream_t st) {
+  if (N <= 0) return 0;
+  const float tfx = width / (2 * fx), tfy = height / (2 * fy);
+  const int nb = (N + PG - 1) / PG;
+  ProfScope ps(K_PRE_BWD, st);
+  GSB_DISPATCH_K3(k3, (k_preprocess_bwd<K3, true><<<nb, PG, 0, st>>>(N, pws, rots, scales, shs, Rcw, tcw, twc, fx, fy,
+                                                                      cx, cy, tfx, tfy, g_us, g_cinv2ds, g_colors,
+                                                                      nullptr, nullptr, nullptr, nullptr, gp)));
   GSB_CUDA_TRY(cudaGetLastError());
   return 0;
 }

@@ -15,7 +15,7 @@ enum KernelId {
   K_PROJECT = 0, K_COV3D, K_COV2D, K_SH2COLOR, K_INVCOV, K_RECTS, K_SCAN, K_KEYS, K_SORT, K_RANGES,
   K_PACK, K_DRAW, K_DRAW_BWD, K_PRE_FWD, K_PRE_BWD, K_FINALIZE, K_LOSS_FWD, K_LOSS_BWD, K_BMM,
   K_DENSITY_ACC, K_DENSITY_CLASSIFY, K_DENSITY_SCAN, K_DENSITY_APPLY, K_RESET_ALPHA, K_GS_DECODE,
-  K_GS_TO_PARAMS, K_PARAMS_TO_GS, K_COUNT
+  K_GS_TO_PARAMS, K_PARAMS_TO_GS, K_GRAD_EXCHANGE, K_COUNT
 };
 struct ProfScope {
   ProfScope(int id, cudaStream_t st);
@@ -48,6 +48,39 @@ int launch_preprocess_bwd(int N, int k3, const float *pws, const float *rots, co
                           float fy, float cx, float cy, float width, float height, const float *g_us,
                           const float *g_cinv2ds, const float *g_colors, float *g_pws, float *g_shs,
                           float *g_scales, float *g_rots, cudaStream_t st);
+
+// ---- multi-GPU gradient exchange (comm.cu; the producer is the PUSH variant in fused.cu).
+// Every rank owns one region of peer-mapped memory:
+//   [control 4 KiB: arrive[8] u32 @0, done[8] u32 @64, counters @128/@132, status @136]
+//   [staging: world slots x (rpr rows x (ks+11) floats), slot s = what rank s pushed here]
+//   [result:  world*rpr rows x (ks+11) floats, the summed gradients, identical on every rank]
+// Rows are split in `world` contiguous ranges of rpr = tiles_per_rank * 128 Gaussians; slot
+// and result keep the SoA segment order shs | rots | pws | scales | alphas.
+constexpr int kMaxWorld = 8;
+constexpr size_t kCtrlBytes = 4096;
+struct ExchangeGeom {
+  int world, ks, tiles_per_rank;
+  long long rpr, rows_total, slot_floats;
+  long long slot_off[5], result_off[5];  // float offsets of the 5 segments inside a slot / the result
+  int seg_k[5];
+  size_t staging_off, result_base, bytes;  // byte offsets inside the region
+};
+ExchangeGeom exchange_geom(int N, int k3, int world);
+struct GradPush {
+  float *slot[kMaxWorld];      // staging slot `rank` on each owner
+  uint32_t *flags[kMaxWorld];  // arrive[] array of each rank
+  uint32_t *counter;
+  const float *g_alphas;
+  long long rpr, off_rots, off_pws, off_scales, off_alphas;
+  int tiles_per_rank, world, rank;
+  uint32_t epoch;
+};
+int launch_preprocess_bwd_push(int N, int k3, const float *pws, const float *rots, const float *scales,
+                               const float *shs, const float *Rcw, const float *tcw, const float *twc, float fx,
+                               float fy, float cx, float cy, float width, float height, const float *g_us,
+                               const float *g_cinv2ds, const float *g_colors, const GradPush &gp, cudaStream_t st);
+int launch_grad_reduce_bcast(const ExchangeGeom &G, int rank, void *const *regions, uint32_t epoch,
+                             cudaStream_t st);
 
 // ---- batched tiny matmul for the reference's Jacobian chain (smallbmm.cu)
 int launch_small_bmm(long long batch, int M, int K, int NN, const float *A, const float *B, int b_shared,

@@ -119,6 +119,14 @@ class GSFunctionFused(torch.autograd.Function):
         dloss_dus, dloss_dcinv2ds, dloss_dalphas, dloss_dcolors = ops.splatB(
             cam.height, cam.width, us, cinv2ds, alphas, depths, colors, contrib, final_tau,
             patch_range_per_tile, gsid_per_patch, dloss_dgammas)
+        ex = getattr(cam, "grad_exchange", None)
+        if ex is not None:
+            # multi-view data parallel (parallel.GradExchange): the per-Gaussian backward pushes
+            # its tiles into peer memory and the gradients come back already summed over ranks
+            # (dloss_dus stays this view's own: it only feeds the densification statistics)
+            g = ex.backward(pws, rots, scales, shs, cam, dloss_dus, dloss_dcinv2ds, dloss_dcolors, dloss_dalphas)
+            return (g["dpws"], g["dshs"], g["dalphas"].reshape(ctx.alpha_shape), g["dscales"], g["drots"],
+                    dloss_dus.squeeze(1), None)
         dpws, dshs, dscales, drots = ops.preprocessB(
             pws, rots, scales, shs, cam.Rcw, cam.tcw, cam.twc, cam.fx, cam.fy, cam.cx, cam.cy,
             cam.width, cam.height, dloss_dus, dloss_dcinv2ds, dloss_dcolors)

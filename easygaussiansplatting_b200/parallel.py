@@ -1,8 +1,17 @@
 """Multi-view data parallelism (not present in the reference, which is single
 process / single GPU).  One process per GPU, Gaussians replicated, one camera per rank per
-step; the only exchange is a SUM all-reduce of the parameter gradients (236 B/Gaussian), issued
-as few large messages so NCCL moves them over NVLink/NVSwitch at full bandwidth.
-Backend-agnostic: `nccl` on the GPUs, `gloo` in the CPU tests."""
+step; the only exchange is the SUM of the parameter gradients (236 B/Gaussian) over ranks.
+
+Two implementations of that exchange:
+  GradExchange      the product path on GPUs: the fused per-Gaussian backward pushes each
+                    gradient tile into the owning GPU's peer memory while it computes
+                    (gsb_preprocess_backward_push) and one kernel sums and broadcasts
+                    (gsb_grad_reduce_broadcast) -- csrc/comm.cu.  torch.distributed only carries
+                    the 64-byte IPC handles at start-up.
+  allreduce_grads   the library baseline: NCCL (or gloo in the CPU tests) all-reduce of the flat
+                    gradient bucket after the backward; bench.py times it beside GradExchange."""
+import ctypes as C
+
 import torch
 import torch.distributed as dist
 
@@ -68,3 +77,134 @@ def allreduce_grads(tensors, group=None, average=False):
             off += n
         nbytes += flat.numel() * flat.element_size()
     return nbytes
+
+
+# ----------------------------------------------------------------------------- fused exchange
+
+def rows_per_rank(N, world, tile=128):
+    """the contiguous range of Gaussians each rank owns in the exchange (csrc/comm.cu
+    exchange_geom): ceil(ceil(N / 128) / world) tiles of 128"""
+    tiles = (N + tile - 1) // tile
+    return max(1, (tiles + world - 1) // world) * tile
+
+
+class _DeviceSpan:
+    """exposes raw device memory to torch.as_tensor through __cuda_array_interface__"""
+
+    def __init__(self, ptr, n_floats):
+        self.__cuda_array_interface__ = {"shape": (n_floats,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+
+
+class GradExchange:
+    """Sum of the fused backward's parameter gradients over `world` ranks through peer memory.
+
+        ex = GradExchange.from_process_group(N, sh_dim3, device)      # once; collective
+        ...
+        grads = ex.backward(pws, rots, scales, shs, cam, dloss_dus, dloss_dcinv2ds, dloss_dcolors,
+                            dloss_dalphas)        # dict dpws dshs dscales drots dalphas, already summed
+
+    The returned tensors are views of this rank's result region and are overwritten by the next
+    call.  `regions` (low-level constructor): device pointers of every rank's region as seen
+    from this process, own region included -- several "ranks" may also live in one process on
+    one GPU (tests), each on its own stream."""
+
+    def __init__(self, N, sh_dim3, world, rank, regions, device, own_region=None, peers=()):
+        from . import _lib
+        self.lib = _lib.load()
+        self.N, self.k3, self.world, self.rank, self.device = int(N), int(sh_dim3), int(world), int(rank), device
+        self.regions = (C.c_void_p * world)(*[C.c_void_p(int(r)) for r in regions])
+        self._own, self._peers = own_region, list(peers)
+        self.epoch = 0
+        self.rows_total = rows_per_rank(self.N, self.world) * self.world
+        base = int(regions[rank])
+        ks = 3 * self.k3
+        self._views = {}
+        for seg, (name, k) in enumerate((("dshs", ks), ("drots", 4), ("dpws", 3), ("dscales", 3), ("dalphas", 1))):
+            off = self.lib.gsb_exchange_result_offset(self.N, self.k3, self.world, seg)
+            t = torch.as_tensor(_DeviceSpan(base + off, self.rows_total * k), device=device)
+            self._views[name] = t.view(self.rows_total, k)[: self.N]
+
+    @staticmethod
+    def region_bytes(N, sh_dim3, world):
+        from . import _lib
+        return _lib.load().gsb_exchange_region_bytes(int(N), int(sh_dim3), int(world))
+
+    @staticmethod
+    def alloc_region(nbytes):
+        """-> (device pointer, 64-byte IPC handle)"""
+        from . import _lib
+        lib = _lib.load()
+        ptr, handle = C.c_void_p(0), (C.c_ubyte * 64)()
+        _lib.check(lib.gsb_comm_alloc(nbytes, C.byref(ptr), handle), lib)
+        return ptr.value, bytes(handle)
+
+    @classmethod
+    def from_process_group(cls, N, sh_dim3, device, group=None):
+        """collective over the process group: every rank allocates its region and opens the
+        others' through CUDA IPC"""
+        from . import _lib
+        lib = _lib.load()
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        with torch.cuda.device(device):
+            own, handle = cls.alloc_region(cls.region_bytes(N, sh_dim3, world))
+            handles = [None] * world
+            dist.all_gather_object(handles, handle, group=group)
+            regions, peers = [], []
+            for r in range(world):
+                if r == rank:
+                    regions.append(own)
+                    continue
+                p = C.c_void_p(0)
+                buf = (C.c_ubyte * 64).from_buffer_copy(handles[r])
+                _lib.check(lib.gsb_comm_open(buf, C.byref(p)), lib)
+                regions.append(p.value)
+                peers.append(p.value)
+            dist.barrier(group=group)
+        return cls(N, sh_dim3, world, rank, regions, device, own_region=own, peers=peers)
+
+    def push(self, pws, rots, scales, shs, cam, dloss_dus, dloss_dcinv2ds, dloss_dcolors, dloss_dalphas):
+        """phase 1: the fused per-Gaussian backward, storing into the owners' staging slots"""
+        from . import _lib
+        from .ops import _chk, _ptr, _stream
+        pws = _chk(pws, "pws", last=3, ndim=2); rots = _chk(rots, "rots", last=4, ndim=2)
+        scales = _chk(scales, "scales", last=3, ndim=2); shs = _chk(shs, "shs", ndim=2)
+        gu = _chk(dloss_dus, "dloss_dus", last=2); gc = _chk(dloss_dcinv2ds, "dloss_dcinv2ds", last=3)
+        gcol = _chk(dloss_dcolors, "dloss_dcolors", last=3); ga = _chk(dloss_dalphas, "dloss_dalphas")
+        N = pws.shape[0]
+        if N != self.N or shs.shape[1] != 3 * self.k3 or ga.numel() != N or gu.numel() != 2 * N:
+            raise ValueError("GradExchange was built for N=%d, sh_dim3=%d" % (self.N, self.k3))
+        self.epoch += 1
+        with torch.cuda.device(pws.device):
+            _lib.check(self.lib.gsb_preprocess_backward_push(
+                N, self.k3, _ptr(pws), _ptr(rots), _ptr(scales), _ptr(shs), _ptr(_chk(cam.Rcw, "Rcw")),
+                _ptr(_chk(cam.tcw, "tcw")), _ptr(_chk(cam.twc, "twc")), float(cam.fx), float(cam.fy), float(cam.cx),
+                float(cam.cy), float(cam.width), float(cam.height), _ptr(gu), _ptr(gc), _ptr(gcol), _ptr(ga),
+                self.world, self.rank, self.regions, self.epoch, _stream()), self.lib)
+
+    def reduce(self):
+        """phase 2: sum the slots of the owned rows, broadcast, wait for the peers' slices"""
+        from . import _lib
+        from .ops import _stream
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.gsb_grad_reduce_broadcast(self.N, self.k3, self.world, self.rank, self.regions,
+                                                          self.epoch, _stream()), self.lib)
+        return self._views
+
+    def backward(self, pws, rots, scales, shs, cam, dloss_dus, dloss_dcinv2ds, dloss_dcolors, dloss_dalphas):
+        self.push(pws, rots, scales, shs, cam, dloss_dus, dloss_dcinv2ds, dloss_dcolors, dloss_dalphas)
+        return self.reduce()
+
+    def status(self):
+        """0 = fine; 1 = a flag wait timed out (a peer never arrived) -- results invalid"""
+        from . import _lib
+        s = C.c_int(0)
+        _lib.check(self.lib.gsb_exchange_status(C.c_void_p(int(self.regions[self.rank])), C.byref(s)), self.lib)
+        return s.value
+
+    def close(self):
+        for p in self._peers:
+            self.lib.gsb_comm_close(C.c_void_p(p))
+        self._peers = []
+        if self._own is not None:
+            self.lib.gsb_comm_free(C.c_void_p(self._own))
+            self._own = None

@@ -228,6 +228,42 @@ int gsb_ply_rows_to_gs(int64_t N, int stride, int sh_dim, const float *rows, con
 int gsb_gs_to_params(int64_t N, int sh_dim, const float *gs_rows, const gsb_gaussians *dst, gsb_stream_t stream);
 int gsb_params_to_gs(int64_t N, const gsb_gaussians *src, float *gs_rows, gsb_stream_t stream);
 
+/* ---- multi-GPU gradient exchange (extension; SURVEY 8e -- the reference is single-GPU).
+ * Multi-view data parallelism: one process per GPU, Gaussians replicated, one camera per rank;
+ * the parameter gradients (dshs, drots, dpws, dscales, dalphas = 3k + 11 floats per Gaussian)
+ * must be summed over ranks.  Instead of an all-reduce after the backward, the fused
+ * per-Gaussian backward PUSHES each gradient tile into peer memory while it computes
+ * (gsb_preprocess_backward_push), and one kernel sums and broadcasts
+ * (gsb_grad_reduce_broadcast).  Protocol, per step, on every rank, same `epoch` (1, 2, 3, ...):
+ *     gsb_preprocess_backward_push(...);  gsb_grad_reduce_broadcast(...);
+ * after which the summed gradients sit in the rank's own region at
+ * gsb_exchange_result_offset(..., segment), segment 0..4 = dshs [R,3k], drots [R,4], dpws [R,3],
+ * dscales [R,3], dalphas [R,1] with R = world * rows-per-rank >= N (rows >= N are padding).
+ *
+ * A "region" is device memory of gsb_exchange_region_bytes(N, sh_dim3, world) bytes obtained
+ * from gsb_comm_alloc (cudaMalloc + zero fill + CUDA IPC handle, GSB_COMM_HANDLE_BYTES bytes);
+ * the handles are exchanged between the processes by the caller (any transport) and opened
+ * with gsb_comm_open.  regions_host[world]: HOST array of device pointers, entry r = rank r's
+ * region as seen from this process (own pointer for r == rank).  world in {1, 2, 4, 8}.
+ * The kernels spin on flags in peer memory with a 5 s timeout; gsb_exchange_status returns 1
+ * if a wait ever timed out (a peer missing) -- the results are then invalid. */
+#define GSB_COMM_HANDLE_BYTES 64
+size_t gsb_exchange_region_bytes(int N, int sh_dim3, int world);
+size_t gsb_exchange_result_offset(int N, int sh_dim3, int world, int segment);
+int gsb_comm_alloc(size_t bytes, void **ptr, void *handle_out);
+int gsb_comm_open(const void *handle, void **peer_ptr);
+int gsb_comm_close(void *peer_ptr);
+int gsb_comm_free(void *ptr);
+int gsb_exchange_status(const void *region, int *status_host);
+int gsb_preprocess_backward_push(int N, int sh_dim3, const float *pws, const float *rots, const float *scales,
+                                 const float *shs, const float *Rcw, const float *tcw, const float *twc,
+                                 float fx, float fy, float cx, float cy, float width, float height,
+                                 const float *dloss_dus, const float *dloss_dcinv2ds, const float *dloss_dcolors,
+                                 const float *dloss_dalphas, int world, int rank, void *const *regions_host,
+                                 uint32_t epoch, gsb_stream_t stream);
+int gsb_grad_reduce_broadcast(int N, int sh_dim3, int world, int rank, void *const *regions_host, uint32_t epoch,
+                              gsb_stream_t stream);
+
 /* ---- options.  "raster_variant": 2 (default) = two pixels per lane with packed f32x2
  * arithmetic (FFMA2/FMUL2/FADD2), 1 = one pixel per lane; same results, kept for A/B
  * measurements.  Also read once from the environment variable GSB_RASTER_VARIANT. */

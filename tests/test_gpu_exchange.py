@@ -1,0 +1,110 @@
+"""Multi-GPU gradient exchange (csrc/comm.cu + the PUSH variant of the fused
+backward): `world` ranks are SIMULATED in one process on one GPU -- every rank has its own
+region (gsb_comm_alloc), its own stream, its own camera and upstream gradients -- so the whole
+protocol (tile ownership, peer stores, arrival / done flags, epoch re-arming, padding rows) runs
+in the ordinary 1-GPU test suite.  The result must equal the rank-ordered sum of what the
+single-GPU backward (ops.preprocessB) returns for each rank, bit for bit.  The CUDA-IPC mapping
+between real processes is exercised by bench.py --gpus N (benchmarks/gpu_extra.sh mgpu)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def t(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+@pytest.mark.parametrize("world,N,k3", [(1, 1000, 16), (2, 1000, 16), (4, 5000, 4), (8, 70001, 16), (2, 128, 1)])
+def test_exchange_equals_rank_ordered_sum(world, N, k3):
+    from easygaussiansplatting_b200 import ops
+    from easygaussiansplatting_b200.gsfunction import Camera
+    from easygaussiansplatting_b200.parallel import GradExchange, rows_per_rank
+    from easygaussiansplatting_b200.scene import ring_camera, synthetic_scene
+    W, H = 320, 200
+    sc = synthetic_scene(N, W, H, sh_dim=3 * k3, seed=world)
+    pws, rots, scales, shs = t(sc["pws"]), t(sc["rots"] * 1.3), t(sc["scales"]), t(sc["shs"])
+    nbytes = GradExchange.region_bytes(N, k3, world)
+    assert nbytes >= 4096 + 2 * world * rows_per_rank(N, world) * (3 * k3 + 11) * 4
+    regions = [GradExchange.alloc_region(nbytes)[0] for _ in range(world)]
+    exs = [GradExchange(N, k3, world, r, regions, DEV, own_region=regions[r]) for r in range(world)]
+    streams = [torch.cuda.Stream() for _ in range(world)]
+    try:
+        for step in range(3):
+            g = torch.Generator(device=DEV).manual_seed(100 * world + step)
+            cams, ins, local = [], [], []
+            for r in range(world):
+                Rcw, tcw, twc = ring_camera(r + step, world + 2)
+                cams.append(Camera(W, H, sc["fx"], sc["fy"], sc["cx"], sc["cy"], t(Rcw), t(tcw), t(twc)))
+                ins.append([torch.randn((N, 1, k), device=DEV, generator=g) for k in (2, 3, 3, 1)])  # us cinv colors alpha
+                gu, gc, gcol, ga = ins[-1]
+                dpws, dshs, dscales, drots = ops.preprocessB(pws, rots, scales, shs, cams[r].Rcw, cams[r].tcw,
+                                                            cams[r].twc, sc["fx"], sc["fy"], sc["cx"], sc["cy"], W, H,
+                                                            gu, gc, gcol)
+                local.append(dict(dpws=dpws, dshs=dshs, dscales=dscales, drots=drots, dalphas=ga.reshape(N, 1)))
+            want = {k: local[0][k].clone() for k in local[0]}
+            for r in range(1, world):
+                for k in want:
+                    want[k] += local[r][k]
+            torch.cuda.synchronize()
+            for r in range(world):
+                with torch.cuda.stream(streams[r]):
+                    exs[r].push(pws, rots, scales, shs, cams[r], *ins[r])
+            if step == 0:
+                torch.cuda.synchronize()          # first step: phases separated; later steps overlap freely
+            outs = []
+            for r in range(world):
+                with torch.cuda.stream(streams[r]):
+                    outs.append(exs[r].reduce())
+            torch.cuda.synchronize()
+            for r in range(world):
+                assert exs[r].status() == 0, "rank %d: a flag wait timed out" % r
+                for k in want:
+                    assert outs[r][k].shape == want[k].shape
+                    assert torch.equal(outs[r][k], want[k]), (step, r, k, float((outs[r][k] - want[k]).abs().max()))
+    finally:
+        for ex in exs:
+            ex.close()
+
+
+def test_exchange_through_autograd_single_rank():
+    """GSFunctionFused with cam.grad_exchange set (world 1) returns the same gradients as without"""
+    from easygaussiansplatting_b200.gsfunction import Camera, GSFunctionFused
+    from easygaussiansplatting_b200.parallel import GradExchange
+    from easygaussiansplatting_b200.scene import synthetic_scene, upstream_gradient
+    N, W, H = 3000, 256, 160
+    sc = synthetic_scene(N, W, H, sh_dim=48, seed=4)
+    cam = Camera(W, H, sc["fx"], sc["fy"], sc["cx"], sc["cy"], t(sc["Rcw"]), t(sc["tcw"]), t(sc["twc"]))
+    dl = t(upstream_gradient(W, H, 4) * (3.0 * W * H))
+    region, _ = GradExchange.alloc_region(GradExchange.region_bytes(N, 16, 1))
+    ex = GradExchange(N, 16, 1, 0, [region], DEV, own_region=region)
+    got = {}
+    try:
+        for mode in ("plain", "exchange"):
+            leaves = [t(sc[k]).requires_grad_() for k in ("pws", "shs")] + [t(sc["alphas"][:, None]).requires_grad_()] + \
+                     [t(sc[k]).requires_grad_() for k in ("scales", "rots")]
+            us = torch.zeros((N, 2), device=DEV, requires_grad=True)
+            cam.grad_exchange = ex if mode == "exchange" else None
+            img, _ = GSFunctionFused.apply(leaves[0], leaves[1], leaves[2], leaves[3], leaves[4], us, cam)
+            img.backward(dl)
+            got[mode] = [p.grad.clone() for p in leaves] + [us.grad.clone()]
+        assert ex.status() == 0
+        for a, b in zip(got["plain"], got["exchange"]):
+            assert torch.equal(a, b)
+    finally:
+        ex.close()
+
+
+def test_exchange_argument_errors():
+    from easygaussiansplatting_b200 import _lib
+    lib = _lib.load()
+    assert lib.gsb_exchange_region_bytes(1000, 16, 9) == 0
+    assert lib.gsb_exchange_region_bytes(1000, 16, 2) > 0
+    import ctypes as C
+    regs = (C.c_void_p * 2)(None, None)
+    rc = lib.gsb_grad_reduce_broadcast(1000, 16, 2, 0, regs, 1, None)
+    assert rc != 0 and b"null region" in lib.gsb_last_error()
+    rc = lib.gsb_grad_reduce_broadcast(1000, 16, 2, 0, regs, 0, None)
+    assert rc != 0
