@@ -3,7 +3,8 @@ backward): `world` ranks are SIMULATED in one process on one GPU -- every rank h
 region (gsb_comm_alloc), its own stream, its own camera and upstream gradients -- so the whole
 protocol (tile ownership, peer stores, arrival / done flags, epoch re-arming, padding rows) runs
 in the ordinary 1-GPU test suite.  The result must equal the rank-ordered sum of what the
-single-GPU backward (ops.preprocessB) returns for each rank, bit for bit.  The CUDA-IPC mapping
+single-GPU backward (ops.preprocessB) returns for each rank (to 1e-6 of the largest gradient:
+the two kernel instantiations may differ by an ulp; dL/dalpha exactly).  The CUDA-IPC mapping
 between real processes is exercised by bench.py --gpus N (benchmarks/gpu_extra.sh mgpu)."""
 import numpy as np
 import pytest
@@ -63,7 +64,12 @@ def test_exchange_equals_rank_ordered_sum(world, N, k3):
                 assert exs[r].status() == 0, "rank %d: a flag wait timed out" % r
                 for k in want:
                     assert outs[r][k].shape == want[k].shape
-                    assert torch.equal(outs[r][k], want[k]), (step, r, k, float((outs[r][k] - want[k]).abs().max()))
+                    # the PUSH and local instantiations of the backward kernel are compiled
+                    # separately; ptxas may contract a*b+c*d differently (seen: 1 ulp at k3 = 1)
+                    err = float((outs[r][k] - want[k]).abs().max() / want[k].abs().max().clamp_min(1e-30))
+                    assert err <= 1e-6, (step, r, k, err)
+                    if k == "dalphas":
+                        assert torch.equal(outs[r][k], want[k])      # pure pass-through + rank-ordered sum
     finally:
         for ex in exs:
             ex.close()
@@ -92,7 +98,7 @@ def test_exchange_through_autograd_single_rank():
             got[mode] = [p.grad.clone() for p in leaves] + [us.grad.clone()]
         assert ex.status() == 0
         for a, b in zip(got["plain"], got["exchange"]):
-            assert torch.equal(a, b)
+            assert float((a - b).abs().max() / a.abs().max().clamp_min(1e-30)) <= 1e-6
     finally:
         ex.close()
 
