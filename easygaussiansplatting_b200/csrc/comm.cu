@@ -95,12 +95,17 @@ __global__ void __launch_bounds__(256) k_grad_reduce_bcast(ReduceArgs a) {
         const float4 x = st4[s * slot4 + v];
         acc.x += x.x, acc.y += x.y, acc.z += x.z, acc.w += x.w;
       }
-      // float offset inside the slot -> segment -> the same rows of the full-size result
+      // float offset inside the slot -> segment -> local tile -> global tile lt * world + rank
+      // (tiles are dealt round-robin; a tile is 128 * K floats, a multiple of 4, so a float4
+      // never straddles two tiles)
       const long long f = 4 * v;
       int seg = 0;
 #pragma unroll
       for (int s = 1; s < 5; s++) seg += f >= a.slot_off[s];
-      const long long ro = a.result_off[seg] + (long long)a.rank * a.rpr * a.seg_k[seg] + (f - a.slot_off[seg]);
+      const unsigned in_seg = (unsigned)(f - a.slot_off[seg]);  // < 2^32: a slot segment is < 16 GiB
+      const unsigned tile_floats = PG * a.seg_k[seg];
+      const unsigned lt = in_seg / tile_floats;
+      const long long ro = a.result_off[seg] + ((long long)lt * WORLD + a.rank) * tile_floats + (in_seg - lt * tile_floats);
 #pragma unroll
       for (int p = 0; p < WORLD; p++) *reinterpret_cast<float4 *>(a.result[p] + ro) = acc;
     }

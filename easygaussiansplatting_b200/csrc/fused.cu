@@ -134,9 +134,11 @@ __global__ void __launch_bounds__(PG) k_preprocess_bwd(
   __syncthreads();
   long long drow = base;
   if (PUSH) {  // destination = slot `rank` on the owner of this tile, rows relative to its range
-    const int owner = (int)(blockIdx.x / gp.tiles_per_rank);
+    // tiles are dealt round-robin over the ranks, so peer and local stores interleave for the
+    // whole kernel instead of one NVLink burst at one end of it
+    const int owner = (int)(blockIdx.x % gp.world);
     float *sb = gp.slot[owner];
-    drow = base - (long long)owner * gp.rpr;
+    drow = (long long)(blockIdx.x / gp.world) * PG;
     g_shs = sb;
     g_rots = sb + gp.off_rots;
     g_pws = sb + gp.off_pws;

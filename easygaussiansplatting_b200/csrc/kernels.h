@@ -54,8 +54,9 @@ int launch_preprocess_bwd(int N, int k3, const float *pws, const float *rots, co
 //   [control 4 KiB: arrive[8] u32 @0, done[8] u32 @64, counters @128/@132, status @136]
 //   [staging: world slots x (rpr rows x (ks+11) floats), slot s = what rank s pushed here]
 //   [result:  world*rpr rows x (ks+11) floats, the summed gradients, identical on every rank]
-// Rows are split in `world` contiguous ranges of rpr = tiles_per_rank * 128 Gaussians; slot
-// and result keep the SoA segment order shs | rots | pws | scales | alphas.
+// Tiles of 128 Gaussians are dealt round-robin: rank r owns global tiles r, r + world, ...
+// (local tile lt <-> global tile lt * world + r), rpr = tiles_per_rank * 128 rows per rank;
+// slot and result keep the SoA segment order shs | rots | pws | scales | alphas.
 constexpr int kMaxWorld = 8;
 constexpr size_t kCtrlBytes = 4096;
 struct ExchangeGeom {

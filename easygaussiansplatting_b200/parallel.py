@@ -82,8 +82,8 @@ def allreduce_grads(tensors, group=None, average=False):
 # ----------------------------------------------------------------------------- fused exchange
 
 def rows_per_rank(N, world, tile=128):
-    """the contiguous range of Gaussians each rank owns in the exchange (csrc/comm.cu
-    exchange_geom): ceil(ceil(N / 128) / world) tiles of 128"""
+    """rows each rank owns in the exchange (csrc/comm.cu exchange_geom): ceil(ceil(N / 128) /
+    world) tiles of 128 Gaussians, dealt round-robin (rank r owns tiles r, r + world, ...)"""
     tiles = (N + tile - 1) // tile
     return max(1, (tiles + world - 1) // world) * tile
 
