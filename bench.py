@@ -420,8 +420,9 @@ def run_ours(args, rank, world):
                                "parameter gradients (fused preprocess fwd/bwd + splat + splatB)",
                    "gaussians": N_GAUSS, "width": WIDTH, "height": HEIGHT, "sh_dim": SH_DIM, "patches": P,
                    "p_eff": p_eff, "views_per_step": world,
-                   "parallelism": ("1 view/rank, shared Gaussians, NCCL all-reduce of param grads"
-                                   if world > 1 else "single GPU"),
+                   "parallelism": ("1 view/rank, shared Gaussians; parameter gradients summed by the fused "
+                                   "peer-memory exchange (push from the backward kernel + reduce/broadcast kernel); "
+                                   "NCCL only carries the IPC handles" if world > 1 else "single GPU"),
                    "l2": "per-step working set (params+grads 0.47 GB, records 0.12 GB, sort buffers) > 126 MB L2; "
                          "no explicit flush"},
         "gaussians_per_s": N_GAUSS * world * args.steps / (ms_dev * 1e-3),
