@@ -31,11 +31,10 @@ SIGNATURES = {
     "gsb_preprocess_forward": (_i, [_i, _i] + [_vp] * 7 + [_f] * 6 + [_vp] * 6),
     "gsb_preprocess_backward": (_i, [_i, _i] + [_vp] * 7 + [_f] * 6 + [_vp] * 8),
     "gsb_splat_bin_workspace_bytes": (_sz, [_i]),
-    "gsb_splat_bin": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _sz, C.POINTER(_i64), C.POINTER(C.c_uint32),
-                           C.POINTER(C.c_int32), _vp]),
+    "gsb_splat_bin": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _sz, C.POINTER(_i64), C.POINTER(C.c_uint32), _vp]),
     "gsb_splat_workspace_bytes": (_sz, [_i, _i, _i, _i64]),
     "gsb_splat_records_offset": (_sz, [_i, _i, _i, _i64]),
-    "gsb_splat_render": (_i, [_i, _i, _i, _i64, C.c_uint32, C.c_int32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _vp,
+    "gsb_splat_render": (_i, [_i, _i, _i, _i64, C.c_uint32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _vp,
                               _vp, _vp, _vp, _vp]),
     "gsb_splat_backward_workspace_bytes": (_sz, [_i, _i, _i, _i64]),
     "gsb_splat_backward": (_i, [_i, _i, _i, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
@@ -84,7 +83,7 @@ def load():
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(lib, name)  # AttributeError if the ABI drifted
             fn.restype, fn.argtypes = res, args
-        if lib.gsb_abi_version() != 2:
+        if lib.gsb_abi_version() != 1:
             raise ImportError("libgsplat_b200.so ABI version mismatch")
         _lib = lib
     return _lib

@@ -48,7 +48,7 @@ static const char *const g_names[K_COUNT] = {"project", "computeCov3D", "compute
                                              "small_bmm", "density_accumulate", "density_classify",
                                              "density_scan(cub)", "density_apply", "reset_alpha",
                                              "ply_rows_to_gs", "gs_to_params", "params_to_gs",
-                                             "grad_reduce_broadcast", "tile_scatter", "tile_sort_pack"};
+                                             "grad_reduce_broadcast"};
 
 ProfScope::ProfScope(int id, cudaStream_t st) : id_(id), st_(st), stop_(nullptr) {
   std::lock_guard<std::mutex> lk(g_prof_mu);
@@ -219,8 +219,7 @@ int gsb_gau_loss(int H, int W, const float *image, const float *gt_image, float 
 size_t gsb_splat_bin_workspace_bytes(int N) { return bin_layout(N).bytes; }
 
 int gsb_splat_bin(int H, int W, int N, const float *us, float *depths, int32_t *areas, void *bin_ws,
-                  size_t bin_ws_bytes, int64_t *P_host, uint32_t *depth_key_max_host,
-                  int32_t *max_tile_patches_host, gsb_stream_t stream) {
+                  size_t bin_ws_bytes, int64_t *P_host, uint32_t *depth_key_max_host, gsb_stream_t stream) {
   GSB_REQUIRE(N >= 0 && H > 0 && W > 0, "splat: bad N/H/W");
   GSB_REQUIRE(P_host != nullptr && bin_ws != nullptr, "splat: null workspace / P_host");
   GSB_REQUIRE(N == 0 || (us && depths && areas), "splat: null pointer");
@@ -229,13 +228,12 @@ int gsb_splat_bin(int H, int W, int N, const float *us, float *depths, int32_t *
   cudaStream_t st = (cudaStream_t)stream;
   int rc = launch_bin(H, W, N, us, depths, areas, bin_ws, L, st);
   if (rc) return rc;
-  uint32_t total[3] = {0, 0, 0};  // [patch count, largest depth key, longest tile list]
-  GSB_CUDA_TRY(cudaMemcpyAsync(total, static_cast<char *>(bin_ws) + L.total, 3 * sizeof(uint32_t),
+  uint32_t total[2] = {0, 0};  // [patch count, largest depth key]
+  GSB_CUDA_TRY(cudaMemcpyAsync(total, static_cast<char *>(bin_ws) + L.total, 2 * sizeof(uint32_t),
                                cudaMemcpyDeviceToHost, st));
   GSB_CUDA_TRY(cudaStreamSynchronize(st));
   *P_host = (int64_t)total[0];
   if (depth_key_max_host) *depth_key_max_host = total[1];
-  if (max_tile_patches_host) *max_tile_patches_host = (int32_t)total[2];
   return 0;
 }
 
@@ -251,9 +249,9 @@ size_t gsb_splat_workspace_bytes(int N, int H, int W, int64_t P) {
   return L.bytes;
 }
 
-int gsb_splat_render(int H, int W, int N, int64_t P, uint32_t depth_key_max, int32_t max_tile_patches,
-                     const float *us, const float *cinv2ds, const float *alphas, const float *depths,
-                     const float *colors, void *bin_ws,
+int gsb_splat_render(int H, int W, int N, int64_t P, uint32_t depth_key_max, const float *us,
+                     const float *cinv2ds, const float *alphas, const float *depths, const float *colors,
+                     const void *bin_ws,
                      void *ws, size_t ws_bytes, float *image, int32_t *contrib, float *final_tau,
                      int32_t *patch_range_per_tile, int32_t *gsid_per_patch, gsb_stream_t stream) {
   GSB_REQUIRE(N >= 0 && H > 0 && W > 0 && P >= 0, "splat: bad N/H/W/P");
@@ -268,7 +266,7 @@ int gsb_splat_render(int H, int W, int N, int64_t P, uint32_t depth_key_max, int
     GSB_REQUIRE(ws_bytes >= SL.bytes, "splat: workspace too small");
   }
   const BinLayout BL = bin_layout(N);
-  int rc = launch_sort_and_pack(H, W, N, P, depth_key_max, max_tile_patches, us, cinv2ds, alphas, depths, colors, bin_ws, BL, ws, SL,
+  int rc = launch_sort_and_pack(H, W, N, P, depth_key_max, us, cinv2ds, alphas, depths, colors, bin_ws, BL, ws, SL,
                                 patch_range_per_tile, gsid_per_patch, st);
   if (rc) return rc;
   const Rec *recs = P > 0 ? reinterpret_cast<const Rec *>(static_cast<char *>(ws) + SL.recs) : nullptr;

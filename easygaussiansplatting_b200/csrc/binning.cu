@@ -12,16 +12,6 @@
 // two fields fit 32 bits the keys are packed as (tile << dbits | depth key) in 32-bit words
 // -- the same (tile, depth-mm, id) order with half the key traffic and 4 instead of 6-8
 // radix passes at 1080p.  Otherwise the 64-bit layout is used.
-//
-// Tile path (default).  The global sort is not needed to get that order: phase 1 also counts
-// the patches of every tile (one atomic per patch) and scans the T counts, which gives P, the
-// per-tile ranges and the longest list; phase 2 scatters (depth key << 32 | id) entries into
-// the tile segments in arrival order and one CTA per tile sorts its segment in shared memory
-// (bitonic, 64-bit keys -> the reference's (depth-mm, id) order exactly, independent of the
-// atomics' order) and packs the records in the same kernel.  That replaces the scan over N,
-// the key emission, 4 radix passes over P pairs, the range search and the separate pack with
-// scatter + sort/pack.  Lists longer than 16384 patches in one tile (or more than 2^18 tiles)
-// take the radix path below.
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
@@ -41,11 +31,9 @@ static inline int bits_for(uint64_t n_values) {  // bits needed to represent 0 .
 __global__ void __launch_bounds__(256) k_rects(int N, const float2 *__restrict__ us,
                                                int2 *__restrict__ areas, float *__restrict__ depths,
                                                int gx, int gy, uint2 *__restrict__ rects,
-                                               uint32_t *__restrict__ counts, uint32_t *__restrict__ max_key,
-                                               uint32_t *__restrict__ tile_counts) {
+                                               uint32_t *__restrict__ counts, uint32_t *__restrict__ max_key) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t n = 0, dk = 0;
-  uint32_t tx0 = 0, ty0 = 0, tw = 0;
   uint2 rect = make_uint2(0u, 0u);
   if (i < N) {
     const float d = depths[i];
@@ -66,25 +54,10 @@ __global__ void __launch_bounds__(256) k_rects(int N, const float2 *__restrict__
       } else {
         rect = make_uint2((uint32_t)x0 | ((uint32_t)x1 << 16), (uint32_t)y0 | ((uint32_t)y1 << 16));
         dk = __float2uint_rz(__fmul_rn(d, 1000.0f));  // kernel.cu:73
-        tx0 = (uint32_t)x0, ty0 = (uint32_t)y0, tw = (uint32_t)(x1 - x0);
       }
     }
     rects[i] = rect;
     counts[i] = n;
-  }
-  if (tile_counts != nullptr) {  // tile path: one count per (Gaussian, tile) pair
-    if (n <= 32) {
-      for (uint32_t t = 0; t < n; t++) atomicAdd(tile_counts + (ty0 + t / tw) * (uint32_t)gx + tx0 + t % tw, 1u);
-    }
-    unsigned big = __ballot_sync(0xffffffffu, n > 32);  // large footprints: the whole warp counts them
-    while (big) {
-      const int src = __ffs(big) - 1;
-      big &= big - 1;
-      const uint32_t bn = __shfl_sync(0xffffffffu, n, src), bw = __shfl_sync(0xffffffffu, tw, src);
-      const uint32_t bx0 = __shfl_sync(0xffffffffu, tx0, src), by0 = __shfl_sync(0xffffffffu, ty0, src);
-      for (uint32_t t = threadIdx.x & 31; t < bn; t += 32)
-        atomicAdd(tile_counts + (by0 + t / bw) * (uint32_t)gx + bx0 + t % bw, 1u);
-    }
   }
   // one atomicMax per CTA (a per-warp atomic on a single address serialises 31k warps)
   __shared__ uint32_t s_max[8];
@@ -162,69 +135,18 @@ __global__ void __launch_bounds__(256) k_ranges(int64_t P, const KeyT *__restric
   if (p == P - 1 || (uint32_t)(keys[p + 1] >> shift) != t) ranges[t].y = (int)(p + 1);
 }
 
-// ---------------------------------------------------------------- tile path kernels
-constexpr int TILE_CAP_MAX = 16384;  // longest per-tile list the shared-memory sort takes
-constexpr int T_CAP = 1 << 18;       // tile arrays reserved in the phase-1 workspace
-
-// total[0] = P, total[2] = longest tile list (total[1] = largest depth key, written by k_rects)
-__global__ void __launch_bounds__(1024) k_tile_total(int T, const uint32_t *__restrict__ starts,
-                                                     const uint32_t *__restrict__ counts,
-                                                     uint32_t *__restrict__ total) {
-  __shared__ uint32_t s_max[32];
-  uint32_t m = 0;
-  for (int t = threadIdx.x; t < T; t += blockDim.x) m = max(m, counts[t]);
-  m = __reduce_max_sync(0xffffffffu, m);
-  if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = m;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int w = 1; w < (int)(blockDim.x >> 5); w++) m = max(m, s_max[w]);
-    total[0] = starts[T - 1] + counts[T - 1];
-    total[2] = m;
-  }
-}
-
-// (depth key << 32 | id) into the tile's segment, in arrival order (the per-tile sort fixes it)
-__global__ void __launch_bounds__(256) k_scatter(int N, const float *__restrict__ depths,
-                                                 const uint2 *__restrict__ rects, int gx,
-                                                 const uint32_t *__restrict__ starts, uint32_t *__restrict__ cursors,
-                                                 uint64_t *__restrict__ entries) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const int lane = threadIdx.x & 31;
-  uint32_t x0 = 0, x1 = 0, y0 = 0, y1 = 0;
-  uint64_t e = 0;
-  if (i < N) {
-    const float d = __ldg(depths + i);
-    if (!(d < MIN_DEPTH)) {
-      const uint2 r = __ldg(rects + i);
-      x0 = r.x & 0xffffu; x1 = r.x >> 16; y0 = r.y & 0xffffu; y1 = r.y >> 16;
-      e = ((uint64_t)__float2uint_rz(__fmul_rn(d, 1000.0f)) << 32) | (uint32_t)i;  // kernel.cu:73
-    }
-  }
-  const uint32_t w = x1 - x0, n = w * (y1 - y0);
-  if (n <= 32) {
-    for (uint32_t t = 0; t < n; t++) {
-      const uint32_t tile = (y0 + t / w) * (uint32_t)gx + x0 + t % w;
-      entries[__ldg(starts + tile) + atomicAdd(cursors + tile, 1u)] = e;
-    }
-  }
-  unsigned big = __ballot_sync(0xffffffffu, n > 32);
-  while (big) {
-    const int src = __ffs(big) - 1;
-    big &= big - 1;
-    const uint32_t bn = __shfl_sync(0xffffffffu, n, src), bw = __shfl_sync(0xffffffffu, w, src);
-    const uint32_t bx0 = __shfl_sync(0xffffffffu, x0, src), by0 = __shfl_sync(0xffffffffu, y0, src);
-    const uint64_t be = __shfl_sync(0xffffffffu, (unsigned long long)e, src);
-    for (uint32_t t = lane; t < bn; t += 32) {
-      const uint32_t tile = (by0 + t / bw) * (uint32_t)gx + bx0 + t % bw;
-      entries[__ldg(starts + tile) + atomicAdd(cursors + tile, 1u)] = be;
-    }
-  }
-}
-
+// Gathers the four per-Gaussian attribute arrays (all L2 resident: 36 B/Gaussian) into the
+// sorted 48-B record stream the rasterizer streams with cp.async.bulk.
 // thr: the per-record bound of the warp-level culling test (common.cuh rec_can_touch); the
-// positive-definiteness check carries a safety factor against fp32 cancellation.
-__device__ __forceinline__ Rec make_record(int g, const float2 *__restrict__ us, const float *__restrict__ cinv2ds,
-                                           const float *__restrict__ alphas, const float *__restrict__ colors) {
+// positive-definiteness check is done in fp64 so the determinant does not cancel.
+__global__ void __launch_bounds__(256) k_pack(int64_t P, const int32_t *__restrict__ gsid,
+                                              const float2 *__restrict__ us,
+                                              const float *__restrict__ cinv2ds,
+                                              const float *__restrict__ alphas,
+                                              const float *__restrict__ colors, Rec *__restrict__ recs) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  const int g = __ldg(gsid + p);
   const float2 u = __ldg(us + g);
   const float A = __ldg(cinv2ds + 3 * (size_t)g), B = __ldg(cinv2ds + 3 * (size_t)g + 1),
               C = __ldg(cinv2ds + 3 * (size_t)g + 2);
@@ -234,6 +156,7 @@ __device__ __forceinline__ Rec make_record(int g, const float2 *__restrict__ us,
   if (al < ALPHA_SKIP) {
     thr = -INFINITY;  // alpha * g < 0.002 everywhere: never contributes
   } else {
+    // positive definite with a safety factor against fp32 cancellation in A C - B^2
     const float ac = A * C;
     const float det = fmaf(A, C, -B * B);
     if (A > 0.f && C > 0.f && det > 1e-4f * ac && ac < 3.0e38f) {
@@ -246,59 +169,7 @@ __device__ __forceinline__ Rec make_record(int g, const float2 *__restrict__ us,
   r.q1 = make_float4(-0.5f * LOG2E * A, -LOG2E * B, -0.5f * LOG2E * C, al);
   r.q2 = make_float4(__ldg(colors + 3 * (size_t)g), __ldg(colors + 3 * (size_t)g + 1),
                      __ldg(colors + 3 * (size_t)g + 2), __int_as_float(g));
-  return r;
-}
-
-// One CTA per tile: segment -> shared memory -> bitonic sort by (depth key, id) -> sorted ids,
-// packed records and the tile's range.  Padding entries are all-ones and sort to the end.
-__global__ void __launch_bounds__(256) k_tile_sort_pack(const uint32_t *__restrict__ starts,
-                                                        const uint32_t *__restrict__ counts,
-                                                        const uint64_t *__restrict__ entries,
-                                                        const float2 *__restrict__ us,
-                                                        const float *__restrict__ cinv2ds,
-                                                        const float *__restrict__ alphas,
-                                                        const float *__restrict__ colors,
-                                                        int2 *__restrict__ ranges, int32_t *__restrict__ gsid,
-                                                        Rec *__restrict__ recs) {
-  extern __shared__ uint64_t s_ent[];
-  const int tile = blockIdx.x, tid = threadIdx.x;
-  const uint32_t L = counts[tile], base = starts[tile];
-  if (tid == 0) ranges[tile] = L ? make_int2((int)base, (int)(base + L)) : make_int2(0, 0);
-  if (L == 0) return;
-  uint32_t n2 = 2;
-  while (n2 < L) n2 <<= 1;
-  for (uint32_t i = tid; i < n2; i += 256) s_ent[i] = i < L ? entries[base + i] : ~0ull;
-  __syncthreads();
-  for (uint32_t k = 2; k <= n2; k <<= 1) {
-    for (uint32_t j = k >> 1; j > 0; j >>= 1) {
-      for (uint32_t i = tid; i < (n2 >> 1); i += 256) {
-        const uint32_t a = ((i & ~(j - 1)) << 1) | (i & (j - 1)), b = a | j;
-        const uint64_t x = s_ent[a], y = s_ent[b];
-        if ((x > y) == ((a & k) == 0)) {
-          s_ent[a] = y;
-          s_ent[b] = x;
-        }
-      }
-      __syncthreads();
-    }
-  }
-  for (uint32_t i = tid; i < L; i += 256) {
-    const int g = (int)(uint32_t)s_ent[i];
-    gsid[base + i] = g;
-    recs[base + i] = make_record(g, us, cinv2ds, alphas, colors);
-  }
-}
-
-// Radix path: gathers the four per-Gaussian attribute arrays (all L2 resident: 36 B/Gaussian)
-// into the sorted 48-B record stream the rasterizer streams with cp.async.bulk.
-__global__ void __launch_bounds__(256) k_pack(int64_t P, const int32_t *__restrict__ gsid,
-                                              const float2 *__restrict__ us,
-                                              const float *__restrict__ cinv2ds,
-                                              const float *__restrict__ alphas,
-                                              const float *__restrict__ colors, Rec *__restrict__ recs) {
-  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= P) return;
-  recs[p] = make_record(__ldg(gsid + p), us, cinv2ds, alphas, colors);
+  recs[p] = r;
 }
 
 // ---------------------------------------------------------------- phase 1
@@ -309,13 +180,9 @@ BinLayout bin_layout(int N) {
   L.rects = o;   o = align_up(o + n * sizeof(uint2), 256);
   L.counts = o;  o = align_up(o + n * sizeof(uint32_t), 256);
   L.offsets = o; o = align_up(o + n * sizeof(uint32_t), 256);
-  L.total = o;   o = align_up(o + 4 * sizeof(uint32_t), 256);  // [P, max depth key, longest tile list]
-  L.tile_counts = o; o = align_up(o + (size_t)T_CAP * sizeof(uint32_t), 256);
-  L.tile_starts = o; o = align_up(o + (size_t)T_CAP * sizeof(uint32_t), 256);
-  size_t tmp = 0, tmp_t = 0;
+  L.total = o;   o = align_up(o + 2 * sizeof(uint32_t), 256);  // [P, max depth key]
+  size_t tmp = 0;
   cub::DeviceScan::InclusiveSum(nullptr, tmp, (uint32_t *)nullptr, (uint32_t *)nullptr, (int)n);
-  cub::DeviceScan::ExclusiveSum(nullptr, tmp_t, (uint32_t *)nullptr, (uint32_t *)nullptr, T_CAP);
-  if (tmp_t > tmp) tmp = tmp_t;
   L.scan_tmp = o;
   L.scan_tmp_bytes = tmp > 0 ? tmp : 256;
   o = align_up(o + L.scan_tmp_bytes, 256);
@@ -323,51 +190,28 @@ BinLayout bin_layout(int N) {
   return L;
 }
 
-bool tile_mode(int H, int W) {
-  const int64_t T = (int64_t)((W + TILE - 1) / TILE) * ((H + TILE - 1) / TILE);
-  return T <= T_CAP;
-}
-
-static int scan_patch_offsets(int N, char *b, const BinLayout &L, cudaStream_t st) {
-  uint32_t *counts = reinterpret_cast<uint32_t *>(b + L.counts);
-  uint32_t *incl = reinterpret_cast<uint32_t *>(b + L.offsets);
-  size_t tmp = L.scan_tmp_bytes;
-  ProfScope ps(K_SCAN, st);
-  GSB_CUDA_TRY(cub::DeviceScan::InclusiveSum(b + L.scan_tmp, tmp, counts, incl, N, st));
-  return 0;
-}
-
-// total[] (device) <- [P, largest depth key, longest tile list (0 = tile path not available)]
 int launch_bin(int H, int W, int N, const float *us, float *depths, int32_t *areas, void *ws,
                const BinLayout &L, cudaStream_t st) {
   char *b = static_cast<char *>(ws);
   uint32_t *total = reinterpret_cast<uint32_t *>(b + L.total);
-  GSB_CUDA_TRY(cudaMemsetAsync(total, 0, 4 * sizeof(uint32_t), st));
+  GSB_CUDA_TRY(cudaMemsetAsync(total, 0, 2 * sizeof(uint32_t), st));
   if (N <= 0) return 0;
   const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
-  const bool tiles = tile_mode(H, W);
-  const int T = gx * gy;
   uint2 *rects = reinterpret_cast<uint2 *>(b + L.rects);
   uint32_t *counts = reinterpret_cast<uint32_t *>(b + L.counts);
-  uint32_t *tile_counts = reinterpret_cast<uint32_t *>(b + L.tile_counts);
-  uint32_t *tile_starts = reinterpret_cast<uint32_t *>(b + L.tile_starts);
-  if (tiles) GSB_CUDA_TRY(cudaMemsetAsync(tile_counts, 0, (size_t)T * sizeof(uint32_t), st));
+  uint32_t *incl = reinterpret_cast<uint32_t *>(b + L.offsets);
   {
     ProfScope ps(K_RECTS, st);
     k_rects<<<(N + 255) / 256, 256, 0, st>>>(N, reinterpret_cast<const float2 *>(us),
                                              reinterpret_cast<int2 *>(areas), depths, gx, gy, rects, counts,
-                                             total + 1, tiles ? tile_counts : nullptr);
+                                             total + 1);
   }
   GSB_CUDA_TRY(cudaGetLastError());
-  if (tiles) {
-    size_t tmp = L.scan_tmp_bytes;
+  size_t tmp = L.scan_tmp_bytes;
+  {
     ProfScope ps(K_SCAN, st);
-    GSB_CUDA_TRY(cub::DeviceScan::ExclusiveSum(b + L.scan_tmp, tmp, tile_counts, tile_starts, T, st));
-    k_tile_total<<<1, 1024, 0, st>>>(T, tile_starts, tile_counts, total);
-  } else {
-    int rc = scan_patch_offsets(N, b, L, st);
-    if (rc) return rc;
-    k_total<<<1, 1, 0, st>>>(N, reinterpret_cast<uint32_t *>(b + L.offsets), total);
+    GSB_CUDA_TRY(cub::DeviceScan::InclusiveSum(b + L.scan_tmp, tmp, counts, incl, N, st));
+    k_total<<<1, 1, 0, st>>>(N, incl, total);
   }
   GSB_CUDA_TRY(cudaGetLastError());
   return 0;
@@ -394,14 +238,12 @@ int sort_layout(int N, int H, int W, int64_t P, SortLayout *out) {
   (void)N;
   SortLayout L{};
   const size_t n = (size_t)(P > 0 ? P : 1);
-  const size_t T = (size_t)((W + TILE - 1) / TILE) * ((H + TILE - 1) / TILE);
   size_t o = 0;
-  L.keys_a = o; o = align_up(o + n * sizeof(uint64_t), 256);  // radix: keys in; tile path: entries
+  L.keys_a = o; o = align_up(o + n * sizeof(uint64_t), 256);
   L.keys_b = o; o = align_up(o + n * sizeof(uint64_t), 256);
   L.vals_a = o; o = align_up(o + n * sizeof(int32_t), 256);
   L.recs = o;   o = align_up(o + n * sizeof(Rec), 256);
   L.counters = o; o = align_up(o + 64, 256);  // persistent-kernel tile counter
-  L.cursors = o; o = align_up(o + (T <= (size_t)T_CAP ? T : 1) * sizeof(uint32_t), 256);
   size_t tmp64 = 0, tmp32 = 0;
   const KeyPlan wide = key_plan(H, W, 0xffffffffu);
   cudaError_t e = cub::DeviceRadixSort::SortPairs(nullptr, tmp64, (uint64_t *)nullptr, (uint64_t *)nullptr,
@@ -457,55 +299,15 @@ static int keys_sort_ranges(int N, int64_t P, const float *depths, const uint32_
   return 0;
 }
 
-static int tile_sort_pack(int N, int T, int gx, int max_tile_patches, const float *us, const float *cinv2ds,
-                          const float *alphas, const float *depths, const float *colors, const char *bb,
-                          const BinLayout &BL, char *b, const SortLayout &SL, int32_t *ranges,
-                          int32_t *gsid_per_patch, cudaStream_t st) {
-  const uint2 *rects = reinterpret_cast<const uint2 *>(bb + BL.rects);
-  const uint32_t *counts = reinterpret_cast<const uint32_t *>(bb + BL.tile_counts);
-  const uint32_t *starts = reinterpret_cast<const uint32_t *>(bb + BL.tile_starts);
-  uint64_t *entries = reinterpret_cast<uint64_t *>(b + SL.keys_a);
-  uint32_t *cursors = reinterpret_cast<uint32_t *>(b + SL.cursors);
-  GSB_CUDA_TRY(cudaMemsetAsync(cursors, 0, (size_t)T * sizeof(uint32_t), st));
-  {
-    ProfScope ps(K_SCATTER, st);
-    k_scatter<<<(N + 255) / 256, 256, 0, st>>>(N, depths, rects, gx, starts, cursors, entries);
-  }
-  GSB_CUDA_TRY(cudaGetLastError());
-  size_t cap = 256;  // elements of shared memory: next power of two >= the longest list
-  while (cap < (size_t)max_tile_patches) cap <<= 1;
-  const size_t smem = cap * sizeof(uint64_t);
-  if (smem > 48 * 1024)
-    GSB_CUDA_TRY(cudaFuncSetAttribute(k_tile_sort_pack, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  {
-    ProfScope ps(K_TILE_SORT, st);
-    k_tile_sort_pack<<<T, 256, smem, st>>>(starts, counts, entries, reinterpret_cast<const float2 *>(us), cinv2ds,
-                                           alphas, colors, reinterpret_cast<int2 *>(ranges), gsid_per_patch,
-                                           reinterpret_cast<Rec *>(b + SL.recs));
-  }
-  GSB_CUDA_TRY(cudaGetLastError());
-  return 0;
-}
-
-// max_tile_patches: the longest tile list phase 1 reported (> 0 selects the tile path when it
-// fits), or <= 0 to force the radix path (bin_ws is then also written: the scan over N).
-int launch_sort_and_pack(int H, int W, int N, int64_t P, uint32_t depth_key_max, int max_tile_patches,
-                         const float *us, const float *cinv2ds, const float *alphas, const float *depths,
-                         const float *colors, void *bin_ws, const BinLayout &BL, void *ws, const SortLayout &SL,
+int launch_sort_and_pack(int H, int W, int N, int64_t P, uint32_t depth_key_max, const float *us,
+                         const float *cinv2ds, const float *alphas, const float *depths, const float *colors,
+                         const void *bin_ws, const BinLayout &BL, void *ws, const SortLayout &SL,
                          int32_t *ranges, int32_t *gsid_per_patch, cudaStream_t st) {
   const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
-  char *bb = static_cast<char *>(bin_ws);
-  char *b = static_cast<char *>(ws);
-  const bool tiles = tile_mode(H, W);
-  if (P > 0 && N > 0 && tiles && max_tile_patches > 0 && max_tile_patches <= TILE_CAP_MAX)
-    return tile_sort_pack(N, gx * gy, gx, max_tile_patches, us, cinv2ds, alphas, depths, colors, bb, BL, b, SL, ranges,
-                          gsid_per_patch, st);
   GSB_CUDA_TRY(cudaMemsetAsync(ranges, 0, sizeof(int32_t) * 2 * (size_t)gx * gy, st));
   if (P <= 0 || N <= 0) return 0;
-  if (tiles) {  // phase 1 skipped the scan over N
-    int rc = scan_patch_offsets(N, bb, BL, st);
-    if (rc) return rc;
-  }
+  const char *bb = static_cast<const char *>(bin_ws);
+  char *b = static_cast<char *>(ws);
   const uint32_t *incl = reinterpret_cast<const uint32_t *>(bb + BL.offsets);
   const uint2 *rects = reinterpret_cast<const uint2 *>(bb + BL.rects);
   const KeyPlan kp = key_plan(H, W, depth_key_max);

@@ -15,7 +15,7 @@ enum KernelId {
   K_PROJECT = 0, K_COV3D, K_COV2D, K_SH2COLOR, K_INVCOV, K_RECTS, K_SCAN, K_KEYS, K_SORT, K_RANGES,
   K_PACK, K_DRAW, K_DRAW_BWD, K_PRE_FWD, K_PRE_BWD, K_FINALIZE, K_LOSS_FWD, K_LOSS_BWD, K_BMM,
   K_DENSITY_ACC, K_DENSITY_CLASSIFY, K_DENSITY_SCAN, K_DENSITY_APPLY, K_RESET_ALPHA, K_GS_DECODE,
-  K_GS_TO_PARAMS, K_PARAMS_TO_GS, K_GRAD_EXCHANGE, K_SCATTER, K_TILE_SORT, K_COUNT
+  K_GS_TO_PARAMS, K_PARAMS_TO_GS, K_GRAD_EXCHANGE, K_COUNT
 };
 struct ProfScope {
   ProfScope(int id, cudaStream_t st);
@@ -112,19 +112,19 @@ int launch_params_to_gs(int64_t N, float *const *src, float *gs, cudaStream_t st
 
 // ---- binning (binning.cu)
 struct BinLayout {  // carve-up of the phase-1 workspace
-  size_t rects, counts, offsets, total, tile_counts, tile_starts, scan_tmp, scan_tmp_bytes, bytes;
+  size_t rects, counts, offsets, total, scan_tmp, scan_tmp_bytes, bytes;
 };
 BinLayout bin_layout(int N);
 int launch_bin(int H, int W, int N, const float *us, float *depths, int32_t *areas, void *ws,
                const BinLayout &L, cudaStream_t st);
 
 struct SortLayout {  // carve-up of the phase-2 workspace
-  size_t keys_a, keys_b, vals_a, recs, counters, cursors, sort_tmp, sort_tmp_bytes, bytes;
+  size_t keys_a, keys_b, vals_a, recs, counters, sort_tmp, sort_tmp_bytes, bytes;
 };
 int sort_layout(int N, int H, int W, int64_t P, SortLayout *out);
-int launch_sort_and_pack(int H, int W, int N, int64_t P, uint32_t depth_key_max, int max_tile_patches,
-                         const float *us, const float *cinv2ds, const float *alphas, const float *depths,
-                         const float *colors, void *bin_ws, const BinLayout &BL, void *ws, const SortLayout &SL,
+int launch_sort_and_pack(int H, int W, int N, int64_t P, uint32_t depth_key_max, const float *us,
+                         const float *cinv2ds, const float *alphas, const float *depths, const float *colors,
+                         const void *bin_ws, const BinLayout &BL, void *ws, const SortLayout &SL,
                          int32_t *ranges, int32_t *gsid_per_patch, cudaStream_t st);
 int launch_pack_only(int64_t P, const int32_t *gsid_per_patch, const float *us, const float *cinv2ds,
                      const float *alphas, const float *colors, Rec *recs, cudaStream_t st);

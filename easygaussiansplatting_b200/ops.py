@@ -178,9 +178,9 @@ def splat(height, width, us, cinv2ds, alphas, depths, colors, areas):
         st = _stream()
         bin_bytes = lib.gsb_splat_bin_workspace_bytes(N)
         bin_ws = torch.empty((bin_bytes,), dtype=torch.uint8, device=dev)
-        P, dkmax, maxlen = C.c_int64(0), C.c_uint32(0), C.c_int32(0)
+        P, dkmax = C.c_int64(0), C.c_uint32(0)
         _lib.check(lib.gsb_splat_bin(H, W, N, _ptr(us), _ptr(depths), _ptr(areas), _ptr(bin_ws), bin_bytes,
-                                     C.byref(P), C.byref(dkmax), C.byref(maxlen), st), lib)
+                                     C.byref(P), C.byref(dkmax), st), lib)
         P = int(P.value)
         ws_bytes = lib.gsb_splat_workspace_bytes(N, H, W, P)
         ws = torch.empty((max(ws_bytes, 1),), dtype=torch.uint8, device=dev)
@@ -189,7 +189,7 @@ def splat(height, width, us, cinv2ds, alphas, depths, colors, areas):
         final_tau = torch.empty((H, W), dtype=torch.float32, device=dev)
         ranges = torch.empty((T, 2), dtype=torch.int32, device=dev)
         gsid = torch.empty((P,), dtype=torch.int32, device=dev)
-        _lib.check(lib.gsb_splat_render(H, W, N, P, dkmax.value, maxlen.value, _ptr(us), _ptr(cinv2ds), _ptr(alphas),
+        _lib.check(lib.gsb_splat_render(H, W, N, P, dkmax.value, _ptr(us), _ptr(cinv2ds), _ptr(alphas),
                                         _ptr(depths), _ptr(colors), _ptr(bin_ws), _ptr(ws), ws_bytes,
                                         _ptr(image), _ptr(contrib), _ptr(final_tau), _ptr(ranges), _ptr(gsid),
                                         st), lib)

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define GSB_ABI_VERSION 2
+#define GSB_ABI_VERSION 1
 #define GSB_TILE 16            /* reference common.cuh:13 BLOCK */
 #define GSB_RECORD_BYTES 48    /* packed per-patch record, see DESIGN.md "data layout" */
 
@@ -96,43 +96,34 @@ int gsb_preprocess_backward(int N, int sh_dim3, const float *pws, const float *r
                             const float *dloss_dcinv2ds, const float *dloss_dcolors, float *dloss_dpws,
                             float *dloss_dshs, float *dloss_dscales, float *dloss_drots, gsb_stream_t stream);
 
-/* ---- splat, phase 1: tile rectangles, per-tile patch counts, patch count.
+/* ---- splat, phase 1: tile rectangles + patch count.
  * Replaces getRects + thrust::inclusive_scan + the D2H read of the total
  * (gausplat.cu:54-67, kernel.cu:82-122).  depths and areas are READ-WRITE (Gaussians that
- * touch no tile get depths = -1, areas = 0).  Leaves rects / per-tile counts and starts in
- * `bin_ws` for phase 2.  After synchronising `stream` (the one host sync; the reference has
- * the same read-back, gausplat.cu:67) writes
- *   *P_host                  the patch count,
- *   *depth_key_max_host      the largest depth key (uint32)(depth*1000) of a binned Gaussian
- *                            (nullable),
- *   *max_tile_patches_host   the longest per-tile patch list (nullable; 0 when the frame has
- *                            more than 2^18 tiles and the per-tile counts were not taken). */
+ * touch no tile get depths = -1, areas = 0).  Leaves rects/offsets in `bin_ws` for phase 2.
+ * Writes the patch count to *P_host and the largest depth key (uint32)(depth*1000) of a
+ * binned Gaussian to *depth_key_max_host (nullable) after synchronising `stream` (the one
+ * host sync; the reference has the same read-back, gausplat.cu:67). */
 size_t gsb_splat_bin_workspace_bytes(int N);
 int gsb_splat_bin(int H, int W, int N, const float *us, float *depths, int32_t *areas,
                   void *bin_ws, size_t bin_ws_bytes, int64_t *P_host, uint32_t *depth_key_max_host,
-                  int32_t *max_tile_patches_host, gsb_stream_t stream);
+                  gsb_stream_t stream);
 
-/* ---- splat, phase 2: per-tile ordering, tile ranges, record packing, draw.
+/* ---- splat, phase 2: keys, duplicate-key radix sort, tile ranges, record packing, draw.
  * Replaces createKeys + thrust::sort_by_key + getRanges + draw (gausplat.cu:69-105,
  * kernel.cu:46-80,125-271).  `alphas` is [N] (or [N,1]).  Outputs: image[3,H,W] planar,
  * contrib[H,W] int32, final_tau[H,W], patch_range_per_tile[T,2] int32 (T = tiles),
- * gsid_per_patch[P] int32 (Gaussian id of every patch in (tile, depth-mm, id) order -- the
- * order the reference's stable 64-bit sort produces).  Every output element is written.
- * max_tile_patches: the value phase 1 returned.  1..16384 selects the tile path (scatter into
- *   per-tile segments + one shared-memory sort per tile, fused with the record packing);
- *   <= 0 or larger selects the global radix sort (`bin_ws` is then also written: the scan
- *   over N that the tile path does not need).  Both give the same order.
- * depth_key_max: the value phase 1 returned; on the radix path it bounds the sort width (keys
- *   are packed into 32 bits when tile and depth bits fit), 0xFFFFFFFF = the reference's full
- *   64-bit layout.
- * After the call the packed 48-B record stream of the P patches sits at
- * ws + gsb_splat_records_offset(...) and may be handed to gsb_splat_backward as
- * `packed_records` while `ws` and the inputs are unchanged. */
+ * gsid_per_patch[P] int32 (Gaussian id of every patch in (tile, depth-mm, id) order).
+ * Every output element is written (no pre-zeroing needed).
+ * depth_key_max: the value phase 1 returned (bounds the sort width; keys are packed into 32
+ * bits when tile and depth bits fit), or 0xFFFFFFFF for the reference's full 64-bit layout --
+ * the resulting order is the same.  After the call the packed 48-B record stream of the P
+ * patches sits at ws + gsb_splat_records_offset(...) and may be handed to
+ * gsb_splat_backward as `packed_records` while `ws` and the inputs are unchanged. */
 size_t gsb_splat_workspace_bytes(int N, int H, int W, int64_t P);
 size_t gsb_splat_records_offset(int N, int H, int W, int64_t P);
-int gsb_splat_render(int H, int W, int N, int64_t P, uint32_t depth_key_max, int32_t max_tile_patches,
-                     const float *us, const float *cinv2ds, const float *alphas, const float *depths,
-                     const float *colors, void *bin_ws, void *ws, size_t ws_bytes, float *image,
+int gsb_splat_render(int H, int W, int N, int64_t P, uint32_t depth_key_max, const float *us,
+                     const float *cinv2ds, const float *alphas, const float *depths, const float *colors,
+                     const void *bin_ws, void *ws, size_t ws_bytes, float *image,
                      int32_t *contrib, float *final_tau, int32_t *patch_range_per_tile,
                      int32_t *gsid_per_patch, gsb_stream_t stream);
 

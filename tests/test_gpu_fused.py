@@ -144,9 +144,8 @@ def test_preprocess_backward_vs_oracle_chain():
 
 
 def test_record_cache_and_key_widths():
-    """splatB reuses the forward's packed records only for untouched inputs; the tile path
-    (default), the 32-bit and the 64-bit radix-sort layouts (gsb_splat_render max_tile_patches /
-    depth_key_max) all give the same patch order, ranges and image."""
+    """splatB reuses the forward's packed records only for untouched inputs; 32- and 64-bit key
+    layouts (gsb_splat_render depth_key_max) give the same patch order."""
     import ctypes as C
     import gsplatcu as g
     from easygaussiansplatting_b200 import _lib, ops
@@ -173,22 +172,17 @@ def test_record_cache_and_key_widths():
     d2, ar2 = d.clone(), ar.clone()
     bin_bytes = lib.gsb_splat_bin_workspace_bytes(N)
     bin_ws = torch.empty(bin_bytes, dtype=torch.uint8, device=DEV)
-    P, dk, ml = C.c_int64(0), C.c_uint32(0), C.c_int32(0)
+    P, dk = C.c_int64(0), C.c_uint32(0)
     _lib.check(lib.gsb_splat_bin(H, W, N, us.data_ptr(), d2.data_ptr(), ar2.data_ptr(), bin_ws.data_ptr(), bin_bytes,
-                                 C.byref(P), C.byref(dk), C.byref(ml), st), lib)
+                                 C.byref(P), C.byref(dk), st), lib)
     P = int(P.value)
     assert P == out[4].numel() and 200 <= dk.value <= 20000
-    lens = (out[3][:, 1] - out[3][:, 0])
-    assert ml.value == int(lens.max()) and int(lens.sum()) == P
     ws_bytes = lib.gsb_splat_workspace_bytes(N, H, W, P)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=DEV)
     img = torch.empty_like(out[0]); con = torch.empty_like(out[1]); ft = torch.empty_like(out[2])
     rg = torch.empty_like(out[3]); gs = torch.empty_like(out[4])
-    for dkey, mtp in ((0xFFFFFFFF, 0), (dk.value, 0), (dk.value, ml.value), (0xFFFFFFFF, 1 << 20)):
-        for x in (img, con, ft, rg, gs):
-            x.fill_(-7)
-        _lib.check(lib.gsb_splat_render(H, W, N, P, dkey, mtp, us.data_ptr(), ci.data_ptr(), al.data_ptr(),
-                                        d2.data_ptr(), col.data_ptr(), bin_ws.data_ptr(), ws.data_ptr(), ws_bytes,
-                                        img.data_ptr(), con.data_ptr(), ft.data_ptr(), rg.data_ptr(), gs.data_ptr(),
-                                        st), lib)
-        assert torch.equal(gs, out[4]) and torch.equal(rg, out[3]) and torch.equal(img, out[0]), (dkey, mtp)
+    _lib.check(lib.gsb_splat_render(H, W, N, P, 0xFFFFFFFF, us.data_ptr(), ci.data_ptr(), al.data_ptr(),
+                                    d2.data_ptr(), col.data_ptr(), bin_ws.data_ptr(), ws.data_ptr(), ws_bytes,
+                                    img.data_ptr(), con.data_ptr(), ft.data_ptr(), rg.data_ptr(), gs.data_ptr(), st),
+               lib)
+    assert torch.equal(gs, out[4]) and torch.equal(rg, out[3]) and torch.equal(img, out[0])

@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
     out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
     exported = sorted(set(re.findall(r" T (gsb_[a-z0-9_]+)", out)))
     assert exported == syms
-    assert lib.gsb_abi_version() == 2
+    assert lib.gsb_abi_version() == 1
     names = [lib.gsb_profile_kernel_name(i).decode() for i in range(lib.gsb_profile_kernels())]
     assert "draw" in names and "draw_backward" in names
 
