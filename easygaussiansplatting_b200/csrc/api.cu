@@ -279,13 +279,14 @@ int gsb_splat_render(int H, int W, int N, int64_t P, uint32_t depth_key_max, con
   // sparse frame (< 48 patches per tile on average): persistent grid + tile queue
   const int64_t T = (int64_t)((W + GSB_TILE - 1) / GSB_TILE) * ((H + GSB_TILE - 1) / GSB_TILE);
   if (P >= 48 * T) tile_counter = nullptr;
-  return launch_draw(H, W, patch_range_per_tile, recs, image, contrib, final_tau, tile_counter, st);
+  return launch_draw(H, W, patch_range_per_tile, recs, gsid_per_patch, image, contrib, final_tau, tile_counter, st);
 }
 
 size_t gsb_splat_backward_workspace_bytes(int N, int H, int W, int64_t P) {
   (void)H; (void)W;
-  // packed records (256-B aligned) + the [N,9] moment accumulators
-  return (size_t)(P > 0 ? P : 1) * sizeof(Rec) + 512 + (size_t)(N > 0 ? N : 1) * 9 * sizeof(float) + 512;
+  // per-Gaussian records (256-B aligned; only when they have to be rebuilt, P > 0) + the [N,9]
+  // moment accumulators
+  return (size_t)(P > 0 && N > 0 ? N : 1) * sizeof(Rec) + 512 + (size_t)(N > 0 ? N : 1) * 9 * sizeof(float) + 512;
 }
 
 int gsb_splat_backward(int H, int W, int N, int64_t P, const float *us, const float *cinv2ds,
@@ -305,7 +306,7 @@ int gsb_splat_backward(int H, int W, int N, int64_t P, const float *us, const fl
   // workspace: [records, 256-B aligned (cp.async.bulk needs 16 B)] [moment rows]
   uintptr_t base = (reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255;
   Rec *recs = reinterpret_cast<Rec *>(base);
-  uintptr_t mbase = (base + (size_t)(P_ws > 0 ? P_ws : 1) * sizeof(Rec) + 255) & ~(uintptr_t)255;
+  uintptr_t mbase = (base + (size_t)(P_ws > 0 ? N : 1) * sizeof(Rec) + 255) & ~(uintptr_t)255;
   float *moments = reinterpret_cast<float *>(mbase);
   int *tile_counter = reinterpret_cast<int *>((mbase + (size_t)N * 9 * sizeof(float) + 255) & ~(uintptr_t)255);
   if (P > 0) {
@@ -316,14 +317,14 @@ int gsb_splat_backward(int H, int W, int N, int64_t P, const float *us, const fl
       GSB_REQUIRE((reinterpret_cast<uintptr_t>(packed_records) & 15) == 0, "splatB: packed_records misaligned");
       recs = const_cast<Rec *>(static_cast<const Rec *>(packed_records));
     } else {
-      int rc = launch_pack_only(P, gsid_per_patch, us, cinv2ds, alphas, colors, recs, st);
+      int rc = launch_pack_only(N, nullptr, us, cinv2ds, alphas, colors, recs, st);
       if (rc) return rc;
     }
   }
   // P == 0: nothing was drawn; the zeroed moment rows finalise to all-zero gradients
   const int64_t T = (int64_t)((W + GSB_TILE - 1) / GSB_TILE) * ((H + GSB_TILE - 1) / GSB_TILE);
   if (P >= 48 * T) tile_counter = nullptr;  // dense frame: one CTA per tile
-  return launch_draw_backward(H, W, N, patch_range_per_tile, P > 0 ? recs : nullptr, contrib, final_tau,
+  return launch_draw_backward(H, W, N, patch_range_per_tile, P > 0 ? recs : nullptr, gsid_per_patch, contrib, final_tau,
                               dloss_dgammas, cinv2ds, moments, tile_counter, dloss_dus, dloss_dcinv2ds,
                               dloss_dalphas, dloss_dcolors, st);
 }

@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(256) k_pack(int64_t P, const int32_t *__restri
                                               const float *__restrict__ colors, Rec *__restrict__ recs) {
   const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= P) return;
-  const int g = __ldg(gsid + p);
+  const int g = gsid != nullptr ? __ldg(gsid + p) : (int)p;  // nullptr: one record per Gaussian
   const float2 u = __ldg(us + g);
   const float A = __ldg(cinv2ds + 3 * (size_t)g), B = __ldg(cinv2ds + 3 * (size_t)g + 1),
               C = __ldg(cinv2ds + 3 * (size_t)g + 2);
@@ -235,14 +235,14 @@ static KeyPlan key_plan(int H, int W, uint32_t depth_key_max) {
 }
 
 int sort_layout(int N, int H, int W, int64_t P, SortLayout *out) {
-  (void)N;
   SortLayout L{};
   const size_t n = (size_t)(P > 0 ? P : 1);
+  const size_t ng = (size_t)(N > 0 ? N : 1);
   size_t o = 0;
   L.keys_a = o; o = align_up(o + n * sizeof(uint64_t), 256);
   L.keys_b = o; o = align_up(o + n * sizeof(uint64_t), 256);
   L.vals_a = o; o = align_up(o + n * sizeof(int32_t), 256);
-  L.recs = o;   o = align_up(o + n * sizeof(Rec), 256);
+  L.recs = o;   o = align_up(o + ng * sizeof(Rec), 256);  // one record per Gaussian
   L.counters = o; o = align_up(o + 64, 256);  // persistent-kernel tile counter
   size_t tmp64 = 0, tmp32 = 0;
   const KeyPlan wide = key_plan(H, W, 0xffffffffu);
@@ -314,7 +314,7 @@ int launch_sort_and_pack(int H, int W, int N, int64_t P, uint32_t depth_key_max,
   int rc = kp.narrow ? keys_sort_ranges<uint32_t>(N, P, depths, incl, rects, gx, kp, b, SL, ranges, gsid_per_patch, st)
                      : keys_sort_ranges<uint64_t>(N, P, depths, incl, rects, gx, kp, b, SL, ranges, gsid_per_patch, st);
   if (rc) return rc;
-  return launch_pack_only(P, gsid_per_patch, us, cinv2ds, alphas, colors, reinterpret_cast<Rec *>(b + SL.recs), st);
+  return launch_pack_only(N, nullptr, us, cinv2ds, alphas, colors, reinterpret_cast<Rec *>(b + SL.recs), st);
 }
 
 }  // namespace gsb

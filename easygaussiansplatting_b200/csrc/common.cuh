@@ -129,6 +129,28 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
+// ---- per-thread 16-byte async copies (gather) tracked by an mbarrier: every thread of the
+// CTA issues its copies and then arrives once; the barrier (initialised with the CTA size)
+// completes the phase when all those copies have landed.
+__device__ __forceinline__ void cp_async16(void *dst_smem, const void *src_gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_mbar_arrive(uint64_t *bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// lane `tid` of a CTA fetches the record of Gaussian g into dst[tid] (if valid) and arrives
+__device__ __forceinline__ void gather_record(Rec *dst, const Rec *__restrict__ recs, int g, bool valid,
+                                              uint64_t *bar, int tid) {
+  if (valid) {
+    const char *s = reinterpret_cast<const char *>(recs + g);
+    char *d = reinterpret_cast<char *>(dst + tid);
+    cp_async16(d, s);
+    cp_async16(d + 16, s + 16);
+    cp_async16(d + 32, s + 32);
+  }
+  cp_async_mbar_arrive(bar);
+}
+
 // 1-D TMA: bytes must be a multiple of 16, both addresses 16-B aligned.
 __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes,
                                          uint64_t *bar) {

@@ -133,16 +133,18 @@ int launch_pack_only(int64_t P, const int32_t *gsid_per_patch, const float *us, 
 // (raster_fwd2.cu / raster_bwd2.cu), 1 = one pixel per lane (raster_fwd.cu / raster_bwd.cu).
 // Set with gsb_set_option("raster_variant", v) or GSB_RASTER_VARIANT in the environment.
 int raster_variant();
-int launch_draw2(int H, int W, const int32_t *ranges, const Rec *recs, float *image, int32_t *contrib,
-                 float *final_tau, int *tile_counter, cudaStream_t st);
-int launch_draw_bwd2_kernel(int H, int W, const int32_t *ranges, const Rec *recs, const int32_t *contrib,
+int launch_draw2(int H, int W, const int32_t *ranges, const Rec *recs, const int32_t *gsid, float *image,
+                 int32_t *contrib, float *final_tau, int *tile_counter, cudaStream_t st);
+int launch_draw_bwd2_kernel(int H, int W, const int32_t *ranges, const Rec *recs, const int32_t *gsid,
+                            const int32_t *contrib,
                             const float *final_tau, const float *dloss_dgammas, float *moments,
                             int *tile_counter, cudaStream_t st);
 
 // ---- rasterizer (raster_fwd.cu / raster_bwd.cu)
-int launch_draw(int H, int W, const int32_t *ranges, const Rec *recs, float *image, int32_t *contrib,
-                float *final_tau, int *tile_counter, cudaStream_t st);
-int launch_draw_backward(int H, int W, int N, const int32_t *ranges, const Rec *recs, const int32_t *contrib,
+int launch_draw(int H, int W, const int32_t *ranges, const Rec *recs, const int32_t *gsid, float *image,
+                int32_t *contrib, float *final_tau, int *tile_counter, cudaStream_t st);
+int launch_draw_backward(int H, int W, int N, const int32_t *ranges, const Rec *recs, const int32_t *gsid,
+                         const int32_t *contrib,
                          const float *final_tau, const float *dloss_dgammas, const float *cinv2ds,
                          float *moments, int *tile_counter, float *dloss_dus, float *dloss_dcinv2ds,
                          float *dloss_dalphas, float *dloss_dcolors, cudaStream_t st);

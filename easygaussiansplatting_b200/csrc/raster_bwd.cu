@@ -215,20 +215,18 @@ __global__ void __launch_bounds__(PG) k_finalize_grads(int N, const float *__res
   if (valid) dalphas[base + tid] = m[5];
 }
 
-int launch_draw_backward(int H, int W, int N, const int32_t *ranges, const Rec *recs, const int32_t *contrib,
+int launch_draw_backward(int H, int W, int N, const int32_t *ranges, const Rec *recs, const int32_t *gsid,
+                         const int32_t *contrib,
                          const float *final_tau, const float *dloss_dgammas, const float *cinv2ds,
                          float *moments, int *tile_counter, float *dloss_dus, float *dloss_dcinv2ds,
                          float *dloss_dalphas, float *dloss_dcolors, cudaStream_t st) {
   const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
   if (gx <= 0 || gy <= 0 || N <= 0) return 0;
   GSB_CUDA_TRY(cudaMemsetAsync(moments, 0, sizeof(float) * MOM * (size_t)N, st));
-  if (recs != nullptr && raster_variant() == 2) {
-    int rc = launch_draw_bwd2_kernel(H, W, ranges, recs, contrib, final_tau, dloss_dgammas, moments, tile_counter, st);
+  if (recs != nullptr) {
+    int rc = launch_draw_bwd2_kernel(H, W, ranges, recs, gsid, contrib, final_tau, dloss_dgammas, moments,
+                                     tile_counter, st);
     if (rc) return rc;
-  } else if (recs != nullptr) {
-    ProfScope ps(K_DRAW_BWD, st);
-    k_draw_bwd<<<gx * gy, 256, 0, st>>>(W, H, gx, reinterpret_cast<const int2 *>(ranges), recs, contrib,
-                                        final_tau, dloss_dgammas, moments);
   }
   GSB_CUDA_TRY(cudaGetLastError());
   {

@@ -46,7 +46,7 @@ __device__ __forceinline__ int slot_of_lane_v2(int lane) {
 
 __global__ void __launch_bounds__(128, 12) k_draw_bwd2(
     int W, int H, int gx, int T, const int2 *__restrict__ ranges, const Rec *__restrict__ recs,
-    const int32_t *__restrict__ contrib, const float *__restrict__ final_tau,
+    const int32_t *__restrict__ gsid, const int32_t *__restrict__ contrib, const float *__restrict__ final_tau,
     const float *__restrict__ dloss_dgammas, float *__restrict__ moments, int *__restrict__ tile_counter) {
   __shared__ Rec sbuf[2][BWD2_BATCH];
   __shared__ __align__(8) uint64_t mbar[2];
@@ -58,8 +58,8 @@ __global__ void __launch_bounds__(128, 12) k_draw_bwd2(
   const int slot = slot_of_lane_v2(lane);
   float *const mom_lane = moments + (slot >= 0 ? slot : 0);
   if (tid == 0) {
-    mbar_init(&mbar[0], 1);
-    mbar_init(&mbar[1], 1);
+    mbar_init(&mbar[0], 128);  // every thread arrives once per stage fill (gather_record)
+    mbar_init(&mbar[1], 128);
     fence_mbar_init();
   }
   uint32_t ph0 = 0, ph1 = 0;  // completed phases of the two stages (block-uniform)
@@ -110,16 +110,12 @@ __global__ void __launch_bounds__(128, 12) k_draw_bwd2(
     const int bmax = max(max(s_wmax[0], s_wmax[1]), max(s_wmax[2], s_wmax[3]));
     if (bmax <= 0) continue;
     const int nbn = (bmax + BWD2_BATCH - 1) / BWD2_BATCH;  // batches [0, nbn) are needed
-    const Rec *src = recs + range.x;
-    if (tid == 0) {
-      for (int bi = 0; bi < 2 && bi < nbn; bi++) {
-        const int b = nbn - 1 - bi;
-        const uint32_t bytes = (uint32_t)min(BWD2_BATCH, len - b * BWD2_BATCH) * (uint32_t)sizeof(Rec);
-        fence_proxy_async();
-        mbar_expect_tx(&mbar[bi], bytes);
-        bulk_g2s(&sbuf[bi][0], src + (size_t)b * BWD2_BATCH, bytes, &mbar[bi]);
-      }
+    const int32_t *ids = gsid + range.x;
+    for (int bi = 0; bi < 2 && bi < nbn; bi++) {  // stage fill = per-thread gather, see raster_fwd2.cu
+      const int o = (nbn - 1 - bi) * BWD2_BATCH + tid;
+      gather_record(&sbuf[bi][0], recs, o < len ? __ldg(ids + o) : 0, o < len, &mbar[bi], tid);
     }
+    int g_pref = (nbn > 2) ? __ldg(ids + (nbn - 3) * BWD2_BATCH + tid) : 0;  // batch nbn-3 is full
 
     const float2 npx = g2(-(float)px, -(float)(px + 1));
     const float fpy = (float)py;
@@ -178,12 +174,9 @@ __global__ void __launch_bounds__(128, 12) k_draw_bwd2(
         }
       }
       __syncthreads();  // every warp is done with stage s
-      if (tid == 0 && bi + 2 < nbn) {
-        const int b2 = nbn - 1 - (bi + 2);
-        const uint32_t bytes = (uint32_t)min(BWD2_BATCH, len - b2 * BWD2_BATCH) * (uint32_t)sizeof(Rec);
-        fence_proxy_async();
-        mbar_expect_tx(&mbar[s], bytes);
-        bulk_g2s(&sbuf[s][0], src + (size_t)b2 * BWD2_BATCH, bytes, &mbar[s]);
+      if (bi + 2 < nbn) {  // batches below the last one are always full
+        gather_record(&sbuf[s][0], recs, g_pref, true, &mbar[s], tid);
+        g_pref = (bi + 3 < nbn) ? __ldg(ids + (nbn - 1 - (bi + 3)) * BWD2_BATCH + tid) : 0;
       }
     }
   }
@@ -191,7 +184,8 @@ __global__ void __launch_bounds__(128, 12) k_draw_bwd2(
 
 int persistent_grid(int T, int ctas_per_sm);  // raster_fwd2.cu
 
-int launch_draw_bwd2_kernel(int H, int W, const int32_t *ranges, const Rec *recs, const int32_t *contrib,
+int launch_draw_bwd2_kernel(int H, int W, const int32_t *ranges, const Rec *recs, const int32_t *gsid,
+                            const int32_t *contrib,
                             const float *final_tau, const float *dloss_dgammas, float *moments,
                             int *tile_counter, cudaStream_t st) {
   const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
@@ -199,7 +193,7 @@ int launch_draw_bwd2_kernel(int H, int W, const int32_t *ranges, const Rec *recs
   if (tile_counter != nullptr) GSB_CUDA_TRY(cudaMemsetAsync(tile_counter, 0, sizeof(int), st));
   ProfScope ps(K_DRAW_BWD, st);
   k_draw_bwd2<<<tile_counter != nullptr ? persistent_grid(T, 12) : T, 128, 0, st>>>(W, H, gx, T, reinterpret_cast<const int2 *>(ranges), recs,
-                                                      contrib, final_tau, dloss_dgammas, moments, tile_counter);
+                                                      gsid, contrib, final_tau, dloss_dgammas, moments, tile_counter);
   GSB_CUDA_TRY(cudaGetLastError());
   return 0;
 }

@@ -116,16 +116,11 @@ __global__ void __launch_bounds__(256) k_draw(int W, int H, int gx, const int2 *
   }
 }
 
-int launch_draw(int H, int W, const int32_t *ranges, const Rec *recs, float *image, int32_t *contrib,
-                float *final_tau, int *tile_counter, cudaStream_t st) {
+int launch_draw(int H, int W, const int32_t *ranges, const Rec *recs, const int32_t *gsid, float *image,
+                int32_t *contrib, float *final_tau, int *tile_counter, cudaStream_t st) {
   const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
   if (gx <= 0 || gy <= 0) return 0;
-  if (raster_variant() == 2) return launch_draw2(H, W, ranges, recs, image, contrib, final_tau, tile_counter, st);
-  ProfScope ps(K_DRAW, st);
-  k_draw<<<gx * gy, 256, 0, st>>>(W, H, gx, reinterpret_cast<const int2 *>(ranges), recs, image, contrib,
-                                  final_tau);
-  GSB_CUDA_TRY(cudaGetLastError());
-  return 0;
+  return launch_draw2(H, W, ranges, recs, gsid, image, contrib, final_tau, tile_counter, st);
 }
 
 }  // namespace gsb

@@ -27,7 +27,8 @@ __device__ __forceinline__ float2 f2s(float a) { return make_float2(a, a); }
 
 template <bool PERSIST>
 __global__ void __launch_bounds__(128) k_draw2(int W, int H, int gx, int T, const int2 *__restrict__ ranges,
-                                               const Rec *__restrict__ recs, float *__restrict__ image,
+                                               const Rec *__restrict__ recs, const int32_t *__restrict__ gsid,
+                                               float *__restrict__ image,
                                                int32_t *__restrict__ contrib, float *__restrict__ final_tau,
                                                int *__restrict__ tile_counter) {
   __shared__ Rec sbuf[2][DRAW2_BATCH];
@@ -38,8 +39,8 @@ __global__ void __launch_bounds__(128) k_draw2(int W, int H, int gx, int T, cons
   const size_t HW = (size_t)H * W;
   const bool vec2 = (W & 1) == 0;  // pixel pairs are 8-byte aligned in every plane
   if (tid == 0) {
-    mbar_init(&mbar[0], 1);
-    mbar_init(&mbar[1], 1);
+    mbar_init(&mbar[0], 128);  // every thread arrives once per stage fill (gather_record)
+    mbar_init(&mbar[1], 128);
     fence_mbar_init();
   }
   uint32_t ph0 = 0, ph1 = 0;  // completed phases of the two stages (block-uniform)
@@ -69,15 +70,14 @@ __global__ void __launch_bounds__(128) k_draw2(int W, int H, int gx, int T, cons
     int cont0 = 0, cont1 = 0;
     if (len > 0) {  // (a tile without patches keeps image 0, contrib 0, tau 0: kernel.cu:182-183)
       const int nb = (len + DRAW2_BATCH - 1) / DRAW2_BATCH;
-      const Rec *src = recs + range.x;
-      if (tid == 0) {
-        for (int b = 0; b < 2 && b < nb; b++) {
-          const uint32_t bytes = (uint32_t)min(DRAW2_BATCH, len - b * DRAW2_BATCH) * (uint32_t)sizeof(Rec);
-          fence_proxy_async();
-          mbar_expect_tx(&mbar[b], bytes);
-          bulk_g2s(&sbuf[b][0], src + (size_t)b * DRAW2_BATCH, bytes, &mbar[b]);
-        }
+      // stage fill = gather: thread t copies the record of the t-th patch of the batch from the
+      // per-Gaussian record array (L2 resident) with three 16-byte cp.async
+      const int32_t *ids = gsid + range.x;
+      for (int b = 0; b < 2 && b < nb; b++) {
+        const bool v = b * DRAW2_BATCH + tid < len;
+        gather_record(&sbuf[b][0], recs, v ? __ldg(ids + b * DRAW2_BATCH + tid) : 0, v, &mbar[b], tid);
       }
+      int g_pref = (2 * DRAW2_BATCH + tid < len) ? __ldg(ids + 2 * DRAW2_BATCH + tid) : 0;  // id for batch 2
       const float2 npx = f2(-(float)px, -(float)(px + 1));
       const float fpy = (float)py;
       const float bx0 = (float)rx0, bx1 = (float)(rx0 + 7), by0 = (float)ry0, by1 = (float)(ry0 + 7);
@@ -139,11 +139,9 @@ __global__ void __launch_bounds__(128) k_draw2(int W, int H, int gx, int T, cons
         // all warps are past stage s -> it may be refilled; also the tile-wide early out
         const int all_done = __syncthreads_and(warp_done ? 1 : 0);
         if (all_done) break;
-        if (tid == 0 && b + 2 < nb) {
-          const uint32_t bytes = (uint32_t)min(DRAW2_BATCH, len - (b + 2) * DRAW2_BATCH) * (uint32_t)sizeof(Rec);
-          fence_proxy_async();
-          mbar_expect_tx(&mbar[s], bytes);
-          bulk_g2s(&sbuf[s][0], src + (size_t)(b + 2) * DRAW2_BATCH, bytes, &mbar[s]);
+        if (b + 2 < nb) {
+          gather_record(&sbuf[s][0], recs, g_pref, (b + 2) * DRAW2_BATCH + tid < len, &mbar[s], tid);
+          g_pref = ((b + 3) * DRAW2_BATCH + tid < len) ? __ldg(ids + (b + 3) * DRAW2_BATCH + tid) : 0;
         }
       }
       // early exit: the next stage's bulk copy is in flight into shared memory -- consume it
@@ -187,8 +185,8 @@ int persistent_grid(int T, int ctas_per_sm) {
   return (int)(T < g ? T : g);
 }
 
-int launch_draw2(int H, int W, const int32_t *ranges, const Rec *recs, float *image, int32_t *contrib,
-                 float *final_tau, int *tile_counter, cudaStream_t st) {
+int launch_draw2(int H, int W, const int32_t *ranges, const Rec *recs, const int32_t *gsid, float *image,
+                 int32_t *contrib, float *final_tau, int *tile_counter, cudaStream_t st) {
   const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
   if (gx <= 0 || gy <= 0) return 0;
   const int T = gx * gy;
@@ -196,10 +194,10 @@ int launch_draw2(int H, int W, const int32_t *ranges, const Rec *recs, float *im
   ProfScope ps(K_DRAW, st);
   if (tile_counter != nullptr)
     k_draw2<true><<<persistent_grid(T, 12), 128, 0, st>>>(W, H, gx, T, reinterpret_cast<const int2 *>(ranges), recs,
-                                                          image, contrib, final_tau, tile_counter);
+                                                          gsid, image, contrib, final_tau, tile_counter);
   else
-    k_draw2<false><<<T, 128, 0, st>>>(W, H, gx, T, reinterpret_cast<const int2 *>(ranges), recs, image, contrib,
-                                      final_tau, tile_counter);
+    k_draw2<false><<<T, 128, 0, st>>>(W, H, gx, T, reinterpret_cast<const int2 *>(ranges), recs, gsid, image,
+                                      contrib, final_tau, tile_counter);
   GSB_CUDA_TRY(cudaGetLastError());
   return 0;
 }
