@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgsplat_b200.so")
+LIB_PATH = os.environ.get("GSB_LIB") or os.path.join(_HERE, "libgsplat_b200.so")  # GSB_LIB: A/B builds
 
 _vp, _i, _f, _i64, _sz = C.c_void_p, C.c_int, C.c_float, C.c_int64, C.c_size_t
 
@@ -60,7 +60,6 @@ SIGNATURES = {
     "gsb_preprocess_backward_push": (_i, [_i, _i] + [_vp] * 7 + [_f] * 6 + [_vp] * 4 + [_i, _i, C.POINTER(_vp),
                                                                                           C.c_uint32, _vp]),
     "gsb_grad_reduce_broadcast": (_i, [_i, _i, _i, _i, C.POINTER(_vp), C.c_uint32, _vp]),
-    "gsb_set_option": (_i, [C.c_char_p, _i]),
     "gsb_profile_enable": (None, [_i]),
     "gsb_profile_kernels": (_i, []),
     "gsb_profile_kernel_name": (C.c_char_p, [_i]),

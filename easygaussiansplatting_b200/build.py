@@ -12,14 +12,18 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(HERE, "_obj")
-LIB = os.path.join(HERE, "libgsplat_b200.so")
-SOURCES = ["api.cu", "pergaussian.cu", "fused.cu", "binning.cu", "raster_fwd.cu", "raster_bwd.cu",
+# A/B builds (benchmarks only): GSB_VARIANT=name + GSB_EXTRA_NVCC_FLAGS="-DX=1 ..." produce
+# libgsplat_b200_<name>.so next to the default library; _lib.py loads it when GSB_LIB points at it.
+VARIANT = os.environ.get("GSB_VARIANT", "")
+OBJ = os.path.join(HERE, "_obj" + ("_" + VARIANT if VARIANT else ""))
+LIB = os.path.join(HERE, "libgsplat_b200%s.so" % ("_" + VARIANT if VARIANT else ""))
+SOURCES = ["api.cu", "pergaussian.cu", "fused.cu", "binning.cu", "raster_bwd.cu",
            "raster_fwd2.cu", "raster_bwd2.cu", "loss.cu", "smallbmm.cu", "density.cu", "comm.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
          "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--expt-relaxed-constexpr",
          "-ccbin", "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"]
+EXTRA = os.environ.get("GSB_EXTRA_NVCC_FLAGS", "").split()
 
 
 def _deps_mtime():
@@ -33,7 +37,7 @@ def _deps_mtime():
 
 def _compile(src, verbose):
     obj = os.path.join(OBJ, src.replace(".cu", ".o"))
-    cmd = [NVCC] + FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
+    cmd = [NVCC] + FLAGS[:-2] + EXTRA + FLAGS[-2:] + ["-c", os.path.join(CSRC, src), "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
     with open(obj + ".log", "w") as f:
         f.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)

@@ -24,16 +24,6 @@ int set_arg_error(const char *msg) {
   return -1;
 }
 
-// ---- options
-static int g_raster_variant = -1;
-int raster_variant() {
-  if (g_raster_variant < 0) {
-    const char *e = getenv("GSB_RASTER_VARIANT");
-    g_raster_variant = (e && e[0] == '1') ? 1 : 2;
-  }
-  return g_raster_variant;
-}
-
 // ---- profiling
 static bool g_prof_on = false;
 static long long g_launches[K_COUNT] = {0};
@@ -124,16 +114,6 @@ int gsb_inverse_cov2d(int N, const float *cov2ds, float *depths, float *cinv2ds,
   GSB_REQUIRE(N >= 0, "inverseCov2D: N < 0");
   GSB_REQUIRE(N == 0 || (cov2ds && depths && cinv2ds && areas), "inverseCov2D: null pointer");
   return launch_inv_cov2d(N, cov2ds, depths, cinv2ds, areas, dcinv2d_dcov2ds, (cudaStream_t)stream);
-}
-
-int gsb_set_option(const char *name, int value) {
-  GSB_REQUIRE(name != nullptr, "set_option: null name");
-  if (strcmp(name, "raster_variant") == 0) {
-    GSB_REQUIRE(value == 1 || value == 2, "raster_variant must be 1 or 2");
-    g_raster_variant = value;
-    return 0;
-  }
-  return set_arg_error("set_option: unknown option");
 }
 
 void gsb_profile_enable(int on) {

@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(256) k_ranges(int64_t P, const KeyT *__restric
 }
 
 // Gathers the four per-Gaussian attribute arrays (all L2 resident: 36 B/Gaussian) into the
-// sorted 48-B record stream the rasterizer streams with cp.async.bulk.
+// 48-B records the rasterizers gather with cp.async (gsid == nullptr: one record per Gaussian).
 // thr: the per-record bound of the warp-level culling test (common.cuh rec_can_touch); the
 // positive-definiteness check is done in fp64 so the determinant does not cancel.
 __global__ void __launch_bounds__(256) k_pack(int64_t P, const int32_t *__restrict__ gsid,

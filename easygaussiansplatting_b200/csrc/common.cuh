@@ -138,19 +138,6 @@ __device__ __forceinline__ void cp_async16(void *dst_smem, const void *src_gmem)
 __device__ __forceinline__ void cp_async_mbar_arrive(uint64_t *bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// lane `tid` of a CTA fetches the record of Gaussian g into dst[tid] (if valid) and arrives
-__device__ __forceinline__ void gather_record(Rec *dst, const Rec *__restrict__ recs, int g, bool valid,
-                                              uint64_t *bar, int tid) {
-  if (valid) {
-    const char *s = reinterpret_cast<const char *>(recs + g);
-    char *d = reinterpret_cast<char *>(dst + tid);
-    cp_async16(d, s);
-    cp_async16(d + 16, s + 16);
-    cp_async16(d + 32, s + 32);
-  }
-  cp_async_mbar_arrive(bar);
-}
-
 // 1-D TMA: bytes must be a multiple of 16, both addresses 16-B aligned.
 __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes,
                                          uint64_t *bar) {
@@ -172,4 +159,36 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
 namespace gsb {
 int set_cuda_error(cudaError_t e, const char *what, const char *file, int line);
 int set_arg_error(const char *msg);
+
+// Stage fill of the rasterizers = a gather: lane `tid` of the 128-thread CTA fetches the 48-byte
+// record of Gaussian g into dst[tid]; `bar` flips when all n_valid records have landed.
+//   GSB_GATHER_BULK = 1: one 48-byte cp.async.bulk (TMA, SASS UBLKCP) per record, completion by
+//                        byte count (mbarrier initialised with 1: thread 0 posts the expected bytes)
+//   GSB_GATHER_BULK = 0: three 16-byte cp.async (LDGSTS) per record, every thread arrives once
+//                        (mbarrier initialised with 128)
+#ifndef GSB_GATHER_BULK
+#define GSB_GATHER_BULK 0
+#endif
+constexpr uint32_t GATHER_ARRIVALS = GSB_GATHER_BULK ? 1 : 128;
+__device__ __forceinline__ void gather_record(Rec *dst, const Rec *__restrict__ recs, int g, bool valid,
+                                              int n_valid, uint64_t *bar, int tid) {
+#if GSB_GATHER_BULK
+  if (tid == 0) mbar_expect_tx(bar, (uint32_t)n_valid * (uint32_t)sizeof(Rec));
+  if (valid) {
+    fence_proxy_async();
+    bulk_g2s(dst + tid, recs + g, (uint32_t)sizeof(Rec), bar);
+  }
+#else
+  (void)n_valid;
+  if (valid) {
+    const char *s = reinterpret_cast<const char *>(recs + g);
+    char *d = reinterpret_cast<char *>(dst + tid);
+    cp_async16(d, s);
+    cp_async16(d + 16, s + 16);
+    cp_async16(d + 32, s + 32);
+  }
+  cp_async_mbar_arrive(bar);
+#endif
+}
+
 }  // namespace gsb

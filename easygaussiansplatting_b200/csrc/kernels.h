@@ -129,18 +129,11 @@ int launch_sort_and_pack(int H, int W, int N, int64_t P, uint32_t depth_key_max,
 int launch_pack_only(int64_t P, const int32_t *gsid_per_patch, const float *us, const float *cinv2ds,
                      const float *alphas, const float *colors, Rec *recs, cudaStream_t st);
 
-// ---- rasterizer variant: 2 (default) = two pixels per lane + packed f32x2 math
-// (raster_fwd2.cu / raster_bwd2.cu), 1 = one pixel per lane (raster_fwd.cu / raster_bwd.cu).
-// Set with gsb_set_option("raster_variant", v) or GSB_RASTER_VARIANT in the environment.
-int raster_variant();
-int launch_draw2(int H, int W, const int32_t *ranges, const Rec *recs, const int32_t *gsid, float *image,
-                 int32_t *contrib, float *final_tau, int *tile_counter, cudaStream_t st);
+// ---- rasterizer (raster_fwd2.cu / raster_bwd2.cu + raster_bwd.cu).  recs: one 48-byte record per
+// Gaussian; gsid: the sorted patch list -- the kernels gather records into their stage buffers.
 int launch_draw_bwd2_kernel(int H, int W, const int32_t *ranges, const Rec *recs, const int32_t *gsid,
-                            const int32_t *contrib,
-                            const float *final_tau, const float *dloss_dgammas, float *moments,
-                            int *tile_counter, cudaStream_t st);
-
-// ---- rasterizer (raster_fwd.cu / raster_bwd.cu)
+                            const int32_t *contrib, const float *final_tau, const float *dloss_dgammas,
+                            float *moments, int *tile_counter, cudaStream_t st);
 int launch_draw(int H, int W, const int32_t *ranges, const Rec *recs, const int32_t *gsid, float *image,
                 int32_t *contrib, float *final_tau, int *tile_counter, cudaStream_t st);
 int launch_draw_backward(int H, int W, int N, const int32_t *ranges, const Rec *recs, const int32_t *gsid,

@@ -1,6 +1,6 @@
 // Backward tile rasterizer, variant 2: two pixels per lane + packed-fp32 (f32x2) math.
 // See raster_fwd2.cu for the mapping (warp = 8x8 pixels, lane = one row position x 2 adjacent
-// pixels, CTA = 4 warps = one 16x16 tile) and raster_bwd.cu for the algorithm (back-to-front
+// pixels, CTA = 4 warps = one 16x16 tile) and the record gather, raster_bwd.cu for the algorithm (back-to-front
 // replay from (final_tau, contrib), nine per-pixel contributions, split-butterfly warp
 // reduction into one RED per (warp, record) on the Gaussian's 36-byte moment row).
 // The two pixels of a lane are added before the warp reduction, so the reduction and the
@@ -11,6 +11,15 @@
 namespace gsb {
 
 constexpr int BWD2_BATCH = 128;
+// A/B (benchmarks/ab_variants.py, config 2): 10 CTAs/SM with 47 registers and no spills beats
+// 12 CTAs/SM at the 40-register cap (0.671 vs 0.693 ms), and loading a batch's Gaussian ids right
+// before the gather beats carrying them in a register across the batch (0.671 vs 0.678 ms).
+#ifndef BWD2_MINBLOCKS
+#define BWD2_MINBLOCKS 10
+#endif
+#ifndef BWD2_PREFETCH_IDS
+#define BWD2_PREFETCH_IDS 0
+#endif
 constexpr int MOM2 = 9;
 
 __device__ __forceinline__ float2 g2(float a, float b) { return make_float2(a, b); }
@@ -44,7 +53,7 @@ __device__ __forceinline__ int slot_of_lane_v2(int lane) {
   return g < MOM2 ? g : -1;
 }
 
-__global__ void __launch_bounds__(128, 12) k_draw_bwd2(
+__global__ void __launch_bounds__(128, BWD2_MINBLOCKS) k_draw_bwd2(
     int W, int H, int gx, int T, const int2 *__restrict__ ranges, const Rec *__restrict__ recs,
     const int32_t *__restrict__ gsid, const int32_t *__restrict__ contrib, const float *__restrict__ final_tau,
     const float *__restrict__ dloss_dgammas, float *__restrict__ moments, int *__restrict__ tile_counter) {
@@ -58,8 +67,8 @@ __global__ void __launch_bounds__(128, 12) k_draw_bwd2(
   const int slot = slot_of_lane_v2(lane);
   float *const mom_lane = moments + (slot >= 0 ? slot : 0);
   if (tid == 0) {
-    mbar_init(&mbar[0], 128);  // every thread arrives once per stage fill (gather_record)
-    mbar_init(&mbar[1], 128);
+    mbar_init(&mbar[0], GATHER_ARRIVALS);  // see gather_record (common.cuh)
+    mbar_init(&mbar[1], GATHER_ARRIVALS);
     fence_mbar_init();
   }
   uint32_t ph0 = 0, ph1 = 0;  // completed phases of the two stages (block-uniform)
@@ -113,9 +122,12 @@ __global__ void __launch_bounds__(128, 12) k_draw_bwd2(
     const int32_t *ids = gsid + range.x;
     for (int bi = 0; bi < 2 && bi < nbn; bi++) {  // stage fill = per-thread gather, see raster_fwd2.cu
       const int o = (nbn - 1 - bi) * BWD2_BATCH + tid;
-      gather_record(&sbuf[bi][0], recs, o < len ? __ldg(ids + o) : 0, o < len, &mbar[bi], tid);
+      gather_record(&sbuf[bi][0], recs, o < len ? __ldg(ids + o) : 0, o < len,
+                    min(BWD2_BATCH, len - (nbn - 1 - bi) * BWD2_BATCH), &mbar[bi], tid);
     }
+#if BWD2_PREFETCH_IDS
     int g_pref = (nbn > 2) ? __ldg(ids + (nbn - 3) * BWD2_BATCH + tid) : 0;  // batch nbn-3 is full
+#endif
 
     const float2 npx = g2(-(float)px, -(float)(px + 1));
     const float fpy = (float)py;
@@ -175,8 +187,13 @@ __global__ void __launch_bounds__(128, 12) k_draw_bwd2(
       }
       __syncthreads();  // every warp is done with stage s
       if (bi + 2 < nbn) {  // batches below the last one are always full
-        gather_record(&sbuf[s][0], recs, g_pref, true, &mbar[s], tid);
+#if BWD2_PREFETCH_IDS
+        gather_record(&sbuf[s][0], recs, g_pref, true, BWD2_BATCH, &mbar[s], tid);
         g_pref = (bi + 3 < nbn) ? __ldg(ids + (nbn - 1 - (bi + 3)) * BWD2_BATCH + tid) : 0;
+#else
+        gather_record(&sbuf[s][0], recs, __ldg(ids + (nbn - 1 - (bi + 2)) * BWD2_BATCH + tid), true, BWD2_BATCH,
+                      &mbar[s], tid);
+#endif
       }
     }
   }

@@ -12,15 +12,19 @@
 // BASELINE config 4) the grid is persistent -- a few CTAs per SM pulling tile indices from an
 // atomic counter -- so the kernel is bounded by HBM writes instead of CTA launch rate; dense
 // frames use one CTA per tile (the caller passes tile_counter = nullptr).
-// The record pipeline (cp.async.bulk + mbarrier stages), the warp-level exact culling test and
-// the semantics (contrib, final_tau, thresholds) are the ones of raster_fwd.cu; per-pixel
-// arithmetic is the same sequence of IEEE operations, so both variants give identical images.
+// Records: one 48-byte record per Gaussian (binning.cu k_pack); a stage of 128 records is filled
+// by a gather -- thread t takes the t-th Gaussian id of the batch from the sorted patch list and
+// issues three 16-byte cp.async tracked by the stage's mbarrier (common.cuh gather_record).
+// Warp-level exact culling (rec_can_touch) drops records that cannot reach the warp's 8x8 block.
 #include "common.cuh"
 #include "kernels.h"
 
 namespace gsb {
 
 constexpr int DRAW2_BATCH = 128;
+#ifndef FWD2_PREFETCH_IDS
+#define FWD2_PREFETCH_IDS 1
+#endif
 
 __device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
 __device__ __forceinline__ float2 f2s(float a) { return make_float2(a, a); }
@@ -39,8 +43,8 @@ __global__ void __launch_bounds__(128) k_draw2(int W, int H, int gx, int T, cons
   const size_t HW = (size_t)H * W;
   const bool vec2 = (W & 1) == 0;  // pixel pairs are 8-byte aligned in every plane
   if (tid == 0) {
-    mbar_init(&mbar[0], 128);  // every thread arrives once per stage fill (gather_record)
-    mbar_init(&mbar[1], 128);
+    mbar_init(&mbar[0], GATHER_ARRIVALS);  // see gather_record (common.cuh)
+    mbar_init(&mbar[1], GATHER_ARRIVALS);
     fence_mbar_init();
   }
   uint32_t ph0 = 0, ph1 = 0;  // completed phases of the two stages (block-uniform)
@@ -75,9 +79,12 @@ __global__ void __launch_bounds__(128) k_draw2(int W, int H, int gx, int T, cons
       const int32_t *ids = gsid + range.x;
       for (int b = 0; b < 2 && b < nb; b++) {
         const bool v = b * DRAW2_BATCH + tid < len;
-        gather_record(&sbuf[b][0], recs, v ? __ldg(ids + b * DRAW2_BATCH + tid) : 0, v, &mbar[b], tid);
+        gather_record(&sbuf[b][0], recs, v ? __ldg(ids + b * DRAW2_BATCH + tid) : 0, v,
+                      min(DRAW2_BATCH, len - b * DRAW2_BATCH), &mbar[b], tid);
       }
+#if FWD2_PREFETCH_IDS
       int g_pref = (2 * DRAW2_BATCH + tid < len) ? __ldg(ids + 2 * DRAW2_BATCH + tid) : 0;  // id for batch 2
+#endif
       const float2 npx = f2(-(float)px, -(float)(px + 1));
       const float fpy = (float)py;
       const float bx0 = (float)rx0, bx1 = (float)(rx0 + 7), by0 = (float)ry0, by1 = (float)(ry0 + 7);
@@ -140,11 +147,18 @@ __global__ void __launch_bounds__(128) k_draw2(int W, int H, int gx, int T, cons
         const int all_done = __syncthreads_and(warp_done ? 1 : 0);
         if (all_done) break;
         if (b + 2 < nb) {
-          gather_record(&sbuf[s][0], recs, g_pref, (b + 2) * DRAW2_BATCH + tid < len, &mbar[s], tid);
+#if FWD2_PREFETCH_IDS
+          gather_record(&sbuf[s][0], recs, g_pref, (b + 2) * DRAW2_BATCH + tid < len,
+                        min(DRAW2_BATCH, len - (b + 2) * DRAW2_BATCH), &mbar[s], tid);
           g_pref = ((b + 3) * DRAW2_BATCH + tid < len) ? __ldg(ids + (b + 3) * DRAW2_BATCH + tid) : 0;
+#else
+          const bool v2 = (b + 2) * DRAW2_BATCH + tid < len;
+          gather_record(&sbuf[s][0], recs, v2 ? __ldg(ids + (b + 2) * DRAW2_BATCH + tid) : 0, v2,
+                        min(DRAW2_BATCH, len - (b + 2) * DRAW2_BATCH), &mbar[s], tid);
+#endif
         }
       }
-      // early exit: the next stage's bulk copy is in flight into shared memory -- consume it
+      // early exit: the next stage's gather is in flight into shared memory -- consume it
       if (b + 1 < nb) {
         if (!PERSIST) {
           mbar_wait(&mbar[(b + 1) & 1], ((b + 1) >> 1) & 1);
@@ -185,7 +199,7 @@ int persistent_grid(int T, int ctas_per_sm) {
   return (int)(T < g ? T : g);
 }
 
-int launch_draw2(int H, int W, const int32_t *ranges, const Rec *recs, const int32_t *gsid, float *image,
+int launch_draw(int H, int W, const int32_t *ranges, const Rec *recs, const int32_t *gsid, float *image,
                  int32_t *contrib, float *final_tau, int *tile_counter, cudaStream_t st) {
   const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
   if (gx <= 0 || gy <= 0) return 0;

@@ -264,11 +264,6 @@ int gsb_preprocess_backward_push(int N, int sh_dim3, const float *pws, const flo
 int gsb_grad_reduce_broadcast(int N, int sh_dim3, int world, int rank, void *const *regions_host, uint32_t epoch,
                               gsb_stream_t stream);
 
-/* ---- options.  "raster_variant": 2 (default) = two pixels per lane with packed f32x2
- * arithmetic (FFMA2/FMUL2/FADD2), 1 = one pixel per lane; same results, kept for A/B
- * measurements.  Also read once from the environment variable GSB_RASTER_VARIANT. */
-int gsb_set_option(const char *name, int value);
-
 /* ---- launch accounting and optional per-kernel timing (no reference counterpart; used by
  * bench.py for `gpu_launches` and the roofline's live CUDA-event kernel durations).
  * Kernel ids 0..gsb_profile_kernels()-1, names from gsb_profile_kernel_name().

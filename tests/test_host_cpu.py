@@ -35,14 +35,16 @@ def test_library_exports_every_declared_symbol():
     assert "draw" in names and "draw_backward" in names
 
 
-def test_library_is_sm100a_with_bulk_async_copy():
-    """the rasterizer stages records with cp.async.bulk (SASS UBLKCP) and is built for sm_100a"""
+def test_library_is_sm100a_with_async_record_gather():
+    """built for sm_100a; the rasterizers stage records with 16-byte async copies tracked by an
+    mbarrier (SASS LDGSTS + LDGSTSBAR arrive-on + SYNCS try-wait) and use packed fp32 math"""
     from easygaussiansplatting_b200 import _lib, build
     build.build()
     r = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True)
     assert "code for sm_100a" in r.stdout
-    assert "UBLKCP" in r.stdout, "bulk async copy missing from the draw kernels"
-    assert "MUFU.EX2" in r.stdout
+    assert "LDGSTS.E.BYPASS.128" in r.stdout and "LDGSTSBAR" in r.stdout, "async record gather missing"
+    assert "SYNCS.PHASECHK" in r.stdout, "mbarrier wait missing"
+    assert "FFMA2" in r.stdout and "MUFU.EX2" in r.stdout
 
 
 def test_ops_refuse_cpu_tensors():
