@@ -36,7 +36,7 @@ extern "C" {
 
 #define GSB_ABI_VERSION 1
 #define GSB_TILE 16            /* reference common.cuh:13 BLOCK */
-#define GSB_RECORD_BYTES 48    /* packed per-patch record, see DESIGN.md "data layout" */
+#define GSB_RECORD_BYTES 48    /* packed per-Gaussian record, see DESIGN.md "data layout" */
 
 typedef void *gsb_stream_t; /* cudaStream_t */
 
@@ -116,8 +116,8 @@ int gsb_splat_bin(int H, int W, int N, const float *us, float *depths, int32_t *
  * Every output element is written (no pre-zeroing needed).
  * depth_key_max: the value phase 1 returned (bounds the sort width; keys are packed into 32
  * bits when tile and depth bits fit), or 0xFFFFFFFF for the reference's full 64-bit layout --
- * the resulting order is the same.  After the call the packed 48-B record stream of the P
- * patches sits at ws + gsb_splat_records_offset(...) and may be handed to
+ * the resulting order is the same.  After the call the N packed 48-B per-Gaussian records the
+ * rasterizers gather from sit at ws + gsb_splat_records_offset(...) and may be handed to
  * gsb_splat_backward as `packed_records` while `ws` and the inputs are unchanged. */
 size_t gsb_splat_workspace_bytes(int N, int H, int W, int64_t P);
 size_t gsb_splat_records_offset(int N, int H, int W, int64_t P);
@@ -130,8 +130,8 @@ int gsb_splat_render(int H, int W, int N, int64_t P, uint32_t depth_key_max, con
 /* ---- splatB.  Replaces `splatB` (ext.cpp:20-32, gausplat.cu:114-159, kernel.cu:809-950).
  * Consumes the forward's contrib / final_tau / patch_range_per_tile / gsid_per_patch.
  * -> dloss_dus[N,1,2], dloss_dcinv2ds[N,1,3], dloss_dalphas[N,1,1], dloss_dcolors[N,1,3]
- * (every element written).  packed_records: NULL (records are re-packed from
- * gsid_per_patch and the four attribute arrays) or the forward's record stream. */
+ * (every element written).  packed_records: NULL (the per-Gaussian records are rebuilt from the
+ * four attribute arrays into `ws`) or the forward's record array. */
 size_t gsb_splat_backward_workspace_bytes(int N, int H, int W, int64_t P);
 int gsb_splat_backward(int H, int W, int N, int64_t P, const float *us, const float *cinv2ds,
                        const float *alphas, const float *colors, const int32_t *contrib,
