@@ -183,13 +183,16 @@ def run_ours(args, rank, world):
     img_host = torch.empty((3, HEIGHT, WIDTH), dtype=torch.float32).pin_memory()
     chk_host = torch.empty(1, dtype=torch.float32).pin_memory()
 
-    # multi-view DP: the parameter gradients are summed over the views.  Product path: the fused
-    # backward pushes its tiles into peer memory + one reduce/broadcast kernel (GradExchange);
-    # the NCCL all-reduce of the same bucket is timed beside it as the library baseline.
-    exchange = None
+    # multi-view DP: the parameter gradients are summed over the views, either by the fused
+    # exchange (the backward kernel pushes its tiles into peer memory + one reduce/broadcast
+    # kernel, parallel.GradExchange) or by an NCCL all-reduce of the flat bucket.  `value` uses
+    # what parallel.prefer_fused_exchange(world) selects (measured: the exchange wins at 2 GPUs,
+    # NCCL's in-switch reduction at 8); both are always timed and reported in `allreduce`.
+    exchange, use_ex = None, False
     if world > 1:
-        from easygaussiansplatting_b200.parallel import GradExchange
+        from easygaussiansplatting_b200.parallel import GradExchange, prefer_fused_exchange
         exchange = GradExchange.from_process_group(N_GAUSS, SH_DIM // 3, dev)
+        use_ex = prefer_fused_exchange(world)
 
     def make_step(F, use_exchange):
         def step(dl):
@@ -203,8 +206,8 @@ def run_ours(args, rank, world):
             return image
         return step
 
-    step_fused, step_ops = make_step(GSFunctionFused, True), make_step(GSFunction, False)
-    step_fused_nccl = make_step(GSFunctionFused, False)
+    step_fused, step_ops = make_step(GSFunctionFused, use_ex), make_step(GSFunction, False)
+    step_fused_other = make_step(GSFunctionFused, not use_ex)   # the gradient sum done the other way
 
     copy_stream = torch.cuda.Stream(device=dev)
     ev_fwd, ev_dl = torch.cuda.Event(), torch.cuda.Event()
@@ -223,7 +226,7 @@ def run_ours(args, rank, world):
             ev_dl.record(copy_stream)
         for p in leaves:
             p.grad = None
-        cam.grad_exchange = exchange
+        cam.grad_exchange = exchange if use_ex else None
         image, _ = GSFunctionFused.apply(params["pws"], params["shs"], alphas, params["scales"], params["rots"],
                                          us0, cam)
         ev_fwd.record(main)
@@ -234,6 +237,8 @@ def run_ours(args, rank, world):
             img_host.copy_(img, non_blocking=True)
         main.wait_event(ev_dl)
         image.backward(dl_dev)
+        if world > 1 and not use_ex:
+            allreduce_grads([p.grad for p in leaves])
         chk_host.copy_(params["pws"].grad.abs().sum().reshape(1), non_blocking=True)
         main.wait_stream(copy_stream)
 
@@ -280,22 +285,26 @@ def run_ours(args, rank, world):
     e2e = pix * args.steps / (ms_e2e * 1e-3) / 1e6
 
     allreduce = None
-    if world > 1:  # the gradient exchange alone (bytes, device time, max over ranks)
-        # same step with the library collective instead of the fused exchange, and the two
-        # results against each other (the exchange sums in rank order; NCCL's order may differ)
-        step_fused_nccl(dl_dev)
+    if world > 1:  # the two ways of summing the gradients, against each other
+        nccl_step = step_fused_other if use_ex else step_fused
+        ex_step = step_fused if use_ex else step_fused_other
+        nccl_step(dl_dev)
         ref_grads = [p.grad.clone() for p in leaves]
         ms_ar = timed(lambda: allreduce_grads([p.grad for p in leaves]), 10, 3)   # grads = flat bucket views
         nbytes = allreduce_grads([p.grad for p in leaves])
-        ms_nccl_step = timed(lambda: step_fused_nccl(dl_dev), max(5, args.steps // 2), 2) / max(5, args.steps // 2)
-        step_fused(dl_dev)
+        n_other = max(5, args.steps // 2)
+        ms_other = timed(lambda: step_fused_other(dl_dev), n_other, 2) / n_other
+        ex_step(dl_dev)
         torch.cuda.synchronize()
         diff = max(float((p.grad - g).abs().max() / g.abs().max().clamp_min(1e-30)) for p, g in zip(leaves, ref_grads))
+        ms_this = ms_dev / args.steps
         allreduce = {"bytes": int(nbytes), "ms": ms_ar / 10,
                      "algbw_GBps": nbytes / (ms_ar / 10 * 1e-3) / 1e9,
-                     "what": "NCCL all-reduce of the flat gradient bucket (library baseline); `value` uses the "
-                             "fused push + reduce/broadcast exchange over peer memory instead",
-                     "step_ms_with_nccl_allreduce": ms_nccl_step, "step_ms_with_fused_exchange": ms_dev / args.steps,
+                     "what": "`ms`: NCCL all-reduce of the flat 236 B/Gaussian gradient bucket alone.  The step is "
+                             "timed with both gradient sums; `value` uses `selected`",
+                     "selected": "fused_exchange" if use_ex else "nccl_allreduce",
+                     "step_ms_with_nccl_allreduce": ms_other if use_ex else ms_this,
+                     "step_ms_with_fused_exchange": ms_this if use_ex else ms_other,
                      "exchange_vs_nccl_max_rel_diff": diff, "exchange_status": exchange.status()}
 
     # ---- per-kernel durations with CUDA events on the launch stream (roofline leg)
@@ -420,9 +429,10 @@ def run_ours(args, rank, world):
                                "parameter gradients (fused preprocess fwd/bwd + splat + splatB)",
                    "gaussians": N_GAUSS, "width": WIDTH, "height": HEIGHT, "sh_dim": SH_DIM, "patches": P,
                    "p_eff": p_eff, "views_per_step": world,
-                   "parallelism": ("1 view/rank, shared Gaussians; parameter gradients summed by the fused "
-                                   "peer-memory exchange (push from the backward kernel + reduce/broadcast kernel); "
-                                   "NCCL only carries the IPC handles" if world > 1 else "single GPU"),
+                   "parallelism": ("1 view/rank, shared Gaussians; parameter gradients summed by " +
+                                   ("the fused peer-memory exchange (push from the backward kernel + reduce/"
+                                    "broadcast kernel)" if use_ex else "an NCCL all-reduce of the flat bucket")
+                                   if world > 1 else "single GPU"),
                    "l2": "per-step working set (params+grads 0.47 GB, records 0.12 GB, sort buffers) > 126 MB L2; "
                          "no explicit flush"},
         "gaussians_per_s": N_GAUSS * world * args.steps / (ms_dev * 1e-3),

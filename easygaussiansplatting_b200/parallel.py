@@ -2,14 +2,14 @@
 process / single GPU).  One process per GPU, Gaussians replicated, one camera per rank per
 step; the only exchange is the SUM of the parameter gradients (236 B/Gaussian) over ranks.
 
-Two implementations of that exchange:
-  GradExchange      the product path on GPUs: the fused per-Gaussian backward pushes each
-                    gradient tile into the owning GPU's peer memory while it computes
-                    (gsb_preprocess_backward_push) and one kernel sums and broadcasts
-                    (gsb_grad_reduce_broadcast) -- csrc/comm.cu.  torch.distributed only carries
-                    the 64-byte IPC handles at start-up.
-  allreduce_grads   the library baseline: NCCL (or gloo in the CPU tests) all-reduce of the flat
-                    gradient bucket after the backward; bench.py times it beside GradExchange."""
+Two implementations of that exchange (prefer_fused_exchange(world) says which one wins where;
+bench.py times both at every world size):
+  GradExchange      the fused per-Gaussian backward pushes each gradient tile into the owning
+                    GPU's peer memory while it computes (gsb_preprocess_backward_push) and one
+                    kernel sums and broadcasts (gsb_grad_reduce_broadcast) -- csrc/comm.cu.
+                    torch.distributed only carries the 64-byte IPC handles at start-up.
+  allreduce_grads   NCCL (or gloo in the CPU tests) all-reduce of the flat gradient bucket after
+                    the backward."""
 import ctypes as C
 
 import torch
@@ -208,3 +208,13 @@ class GradExchange:
         if self._own is not None:
             self.lib.gsb_comm_free(C.c_void_p(self._own))
             self._own = None
+
+
+def prefer_fused_exchange(world):
+    """Which gradient sum a training loop should use on `world` B200s of one NVSwitch node,
+    from the measurements in profiles/ (bench.py times both at every world size):
+    2 GPUs: GradExchange 1.876 ms/step vs 1.967 ms with NCCL (push hides under the backward,
+    peer stores at ~500 GB/s); 8 GPUs: NCCL's in-switch (NVLS) reduction 2.075 ms vs 2.165 ms --
+    with 7/8 of the bucket leaving every GPU in each phase the exchange is NVLink-bound and has
+    only a 0.1 ms kernel to hide under.  4 GPUs is not measured; NCCL is assumed."""
+    return world == 2
