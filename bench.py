@@ -344,8 +344,13 @@ def run_ours(args, rank, world):
     roof_k = top if top in alg else "draw_backward"
     peak, peak_src = peaks()
     achieved = alg[roof_k] / (kern[roof_k] * 1e-3) / 1e9
+    traffic, traffic_src = None, None   # dram__bytes_read + write per launch from the committed ncu capture
+    tpath = os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")
+    if os.path.exists(tpath):
+        tj = json.load(open(tpath))
+        traffic, traffic_src = tj.get(roof_k), tj.get("source")
     roofline = {"bound": "hbm", "kernel": roof_k, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg[roof_k], "kernel_ms": kern[roof_k],
                 "note": "draw/draw_backward are issue-bound on dense scenes (SURVEY 8d: ~140 flop/B); "
                         "profiles/ holds the ncu pipe utilisation and dram__bytes"}
