@@ -28,17 +28,17 @@ SIGNATURES = {
     "gsb_compute_cov2d": (_i, [_i, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _vp, _vp, _vp, _vp]),
     "gsb_sh2color": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gsb_inverse_cov2d": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp]),
-    "gsb_preprocess_forward": (_i, [_i, _i] + [_vp] * 7 + [_f] * 6 + [_vp] * 6),
-    "gsb_preprocess_backward": (_i, [_i, _i] + [_vp] * 7 + [_f] * 6 + [_vp] * 8),
+    "gsb_preprocess_forward": (_i, [_i, _i] + [_vp] * 7 + [_f] * 6 + [_vp] * 8),
+    "gsb_preprocess_backward": (_i, [_i, _i] + [_vp] * 7 + [_f] * 6 + [_vp] * 12),
     "gsb_splat_bin_workspace_bytes": (_sz, [_i]),
     "gsb_splat_bin": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _sz, C.POINTER(_i64), C.POINTER(C.c_uint32), _vp]),
     "gsb_splat_workspace_bytes": (_sz, [_i, _i, _i, _i64]),
     "gsb_splat_records_offset": (_sz, [_i, _i, _i, _i64]),
-    "gsb_splat_render": (_i, [_i, _i, _i, _i64, C.c_uint32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _vp,
+    "gsb_splat_render": (_i, [_i, _i, _i, _i64, C.c_uint32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _vp,
                               _vp, _vp, _vp, _vp]),
     "gsb_splat_backward_workspace_bytes": (_sz, [_i, _i, _i, _i64]),
     "gsb_splat_backward": (_i, [_i, _i, _i, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
-                                _sz, _vp, _vp, _vp, _vp, _vp]),
+                                _sz, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gsb_small_bmm": (_i, [C.c_longlong, _i, _i, _i, _vp, _vp, _i, _vp, _vp]),
     "gsb_gau_loss_workspace_bytes": (_sz, [_i, _i]),
     "gsb_gau_loss": (_i, [_i, _i, _vp, _vp, _f, _vp, _vp, _vp, _sz, _vp]),
@@ -57,7 +57,7 @@ SIGNATURES = {
     "gsb_comm_close": (_i, [_vp]),
     "gsb_comm_free": (_i, [_vp]),
     "gsb_exchange_status": (_i, [_vp, C.POINTER(_i)]),
-    "gsb_preprocess_backward_push": (_i, [_i, _i] + [_vp] * 7 + [_f] * 6 + [_vp] * 4 + [_i, _i, C.POINTER(_vp),
+    "gsb_preprocess_backward_push": (_i, [_i, _i] + [_vp] * 7 + [_f] * 6 + [_vp] * 7 + [_i, _i, C.POINTER(_vp),
                                                                                           C.c_uint32, _vp]),
     "gsb_grad_reduce_broadcast": (_i, [_i, _i, _i, _i, C.POINTER(_vp), C.c_uint32, _vp]),
     "gsb_profile_enable": (None, [_i]),

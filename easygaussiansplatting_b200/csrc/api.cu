@@ -152,23 +152,40 @@ int gsb_profile_read(int id, double *ms_total, long long *timed_launches) {
 int gsb_preprocess_forward(int N, int sh_dim3, const float *pws, const float *rots, const float *scales,
                            const float *shs, const float *Rcw, const float *tcw, const float *twc, float fx,
                            float fy, float cx, float cy, float width, float height, float *us,
-                           float *cinv2ds, float *colors, float *depths, int32_t *areas, gsb_stream_t stream) {
+                           float *cinv2ds, float *colors, float *depths, int32_t *areas, const float *alphas,
+                           void *records, gsb_stream_t stream) {
   GSB_REQUIRE(N >= 0, "preprocess: N < 0");
+  GSB_REQUIRE((alphas == nullptr) == (records == nullptr), "preprocess: alphas and records go together");
+  GSB_REQUIRE((reinterpret_cast<uintptr_t>(records) & 15) == 0, "preprocess: records misaligned");
   GSB_REQUIRE(sh_dim3 == 1 || sh_dim3 == 4 || sh_dim3 == 9 || sh_dim3 == 16,
               "preprocess: shs.shape[1]/3 must be 1, 4, 9 or 16");
   GSB_REQUIRE(N == 0 || (pws && rots && scales && shs && Rcw && tcw && twc && us && cinv2ds && colors &&
                          depths && areas),
               "preprocess: null pointer");
   return launch_preprocess_fwd(N, sh_dim3, pws, rots, scales, shs, Rcw, tcw, twc, fx, fy, cx, cy, width, height,
-                               us, cinv2ds, colors, depths, areas, (cudaStream_t)stream);
+                               us, cinv2ds, colors, depths, areas, alphas, static_cast<Rec *>(records),
+                               (cudaStream_t)stream);
 }
 
 int gsb_preprocess_backward(int N, int sh_dim3, const float *pws, const float *rots, const float *scales,
                             const float *shs, const float *Rcw, const float *tcw, const float *twc, float fx,
                             float fy, float cx, float cy, float width, float height, const float *dloss_dus,
                             const float *dloss_dcinv2ds, const float *dloss_dcolors, float *dloss_dpws,
-                            float *dloss_dshs, float *dloss_dscales, float *dloss_drots, gsb_stream_t stream) {
+                            float *dloss_dshs, float *dloss_dscales, float *dloss_drots, const float *moments,
+                            const float *cinv2ds, float *dloss_dus_out, float *dloss_dalphas_out,
+                            gsb_stream_t stream) {
   GSB_REQUIRE(N >= 0, "preprocessB: N < 0");
+  if (moments != nullptr) {  // upstream gradients as moment rows (gsb_splat_backward with moments_out)
+    GSB_REQUIRE(sh_dim3 == 1 || sh_dim3 == 4 || sh_dim3 == 9 || sh_dim3 == 16,
+                "preprocessB: shs.shape[1]/3 must be 1, 4, 9 or 16");
+    GSB_REQUIRE(N == 0 || (pws && rots && scales && shs && Rcw && tcw && twc && cinv2ds && dloss_dus_out &&
+                           dloss_dalphas_out && dloss_dpws && dloss_dshs && dloss_dscales && dloss_drots),
+                "preprocessB: null pointer");
+    const MomentsIn mi{moments, cinv2ds, dloss_dus_out, dloss_dalphas_out};
+    return launch_preprocess_bwd(N, sh_dim3, pws, rots, scales, shs, Rcw, tcw, twc, fx, fy, cx, cy, width, height,
+                                 nullptr, nullptr, nullptr, dloss_dpws, dloss_dshs, dloss_dscales, dloss_drots, &mi,
+                                 (cudaStream_t)stream);
+  }
   GSB_REQUIRE(sh_dim3 == 1 || sh_dim3 == 4 || sh_dim3 == 9 || sh_dim3 == 16,
               "preprocessB: shs.shape[1]/3 must be 1, 4, 9 or 16");
   GSB_REQUIRE(N == 0 || (pws && rots && scales && shs && Rcw && tcw && twc && dloss_dus && dloss_dcinv2ds &&
@@ -176,7 +193,7 @@ int gsb_preprocess_backward(int N, int sh_dim3, const float *pws, const float *r
               "preprocessB: null pointer");
   return launch_preprocess_bwd(N, sh_dim3, pws, rots, scales, shs, Rcw, tcw, twc, fx, fy, cx, cy, width, height,
                                dloss_dus, dloss_dcinv2ds, dloss_dcolors, dloss_dpws, dloss_dshs, dloss_dscales,
-                               dloss_drots, (cudaStream_t)stream);
+                               dloss_drots, nullptr, (cudaStream_t)stream);
 }
 
 int gsb_small_bmm(long long batch, int m, int k, int n, const float *A, const float *B, int b_shared, float *C,
@@ -231,7 +248,7 @@ size_t gsb_splat_workspace_bytes(int N, int H, int W, int64_t P) {
 
 int gsb_splat_render(int H, int W, int N, int64_t P, uint32_t depth_key_max, const float *us,
                      const float *cinv2ds, const float *alphas, const float *depths, const float *colors,
-                     const void *bin_ws,
+                     const void *packed_records, const void *bin_ws,
                      void *ws, size_t ws_bytes, float *image, int32_t *contrib, float *final_tau,
                      int32_t *patch_range_per_tile, int32_t *gsid_per_patch, gsb_stream_t stream) {
   GSB_REQUIRE(N >= 0 && H > 0 && W > 0 && P >= 0, "splat: bad N/H/W/P");
@@ -246,10 +263,12 @@ int gsb_splat_render(int H, int W, int N, int64_t P, uint32_t depth_key_max, con
     GSB_REQUIRE(ws_bytes >= SL.bytes, "splat: workspace too small");
   }
   const BinLayout BL = bin_layout(N);
+  GSB_REQUIRE((reinterpret_cast<uintptr_t>(packed_records) & 15) == 0, "splat: packed_records misaligned");
   int rc = launch_sort_and_pack(H, W, N, P, depth_key_max, us, cinv2ds, alphas, depths, colors, bin_ws, BL, ws, SL,
-                                patch_range_per_tile, gsid_per_patch, st);
+                                patch_range_per_tile, gsid_per_patch, packed_records == nullptr, st);
   if (rc) return rc;
   const Rec *recs = P > 0 ? reinterpret_cast<const Rec *>(static_cast<char *>(ws) + SL.recs) : nullptr;
+  if (P > 0 && packed_records != nullptr) recs = static_cast<const Rec *>(packed_records);
   // with P == 0 the workspace may be a dummy: every tile is empty, any variant just writes zeros
   int *tile_counter = P > 0 ? reinterpret_cast<int *>(static_cast<char *>(ws) + SL.counters) : nullptr;
   if (tile_counter == nullptr) {
@@ -274,9 +293,10 @@ int gsb_splat_backward(int H, int W, int N, int64_t P, const float *us, const fl
                        const float *final_tau, const int32_t *patch_range_per_tile,
                        const int32_t *gsid_per_patch, const float *dloss_dgammas,
                        const void *packed_records, void *ws, size_t ws_bytes, float *dloss_dus, float *dloss_dcinv2ds, float *dloss_dalphas,
-                       float *dloss_dcolors, gsb_stream_t stream) {
+                       float *dloss_dcolors, float *moments_out, gsb_stream_t stream) {
   GSB_REQUIRE(N >= 0 && H > 0 && W > 0 && P >= 0, "splatB: bad N/H/W/P");
-  GSB_REQUIRE(N == 0 || (dloss_dus && dloss_dcinv2ds && dloss_dalphas && dloss_dcolors), "splatB: null output");
+  GSB_REQUIRE(N == 0 || moments_out || (dloss_dus && dloss_dcinv2ds && dloss_dalphas && dloss_dcolors),
+              "splatB: null output");
   cudaStream_t st = (cudaStream_t)stream;
   if (N == 0) return 0;
   GSB_REQUIRE(cinv2ds && ws, "splatB: null pointer");
@@ -287,7 +307,7 @@ int gsb_splat_backward(int H, int W, int N, int64_t P, const float *us, const fl
   uintptr_t base = (reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255;
   Rec *recs = reinterpret_cast<Rec *>(base);
   uintptr_t mbase = (base + (size_t)(P_ws > 0 ? N : 1) * sizeof(Rec) + 255) & ~(uintptr_t)255;
-  float *moments = reinterpret_cast<float *>(mbase);
+  float *moments = moments_out != nullptr ? moments_out : reinterpret_cast<float *>(mbase);
   int *tile_counter = reinterpret_cast<int *>((mbase + (size_t)N * 9 * sizeof(float) + 255) & ~(uintptr_t)255);
   if (P > 0) {
     GSB_REQUIRE(us && alphas && colors && contrib && final_tau && patch_range_per_tile && gsid_per_patch &&
@@ -306,7 +326,7 @@ int gsb_splat_backward(int H, int W, int N, int64_t P, const float *us, const fl
   if (P >= 48 * T) tile_counter = nullptr;  // dense frame: one CTA per tile
   return launch_draw_backward(H, W, N, patch_range_per_tile, P > 0 ? recs : nullptr, gsid_per_patch, contrib, final_tau,
                               dloss_dgammas, cinv2ds, moments, tile_counter, dloss_dus, dloss_dcinv2ds,
-                              dloss_dalphas, dloss_dcolors, st);
+                              dloss_dalphas, dloss_dcolors, moments_out == nullptr, st);
 }
 
 // ---- density control + record conversion (density.cu)
@@ -450,14 +470,16 @@ int gsb_preprocess_backward_push(int N, int sh_dim3, const float *pws, const flo
                                  const float *shs, const float *Rcw, const float *tcw, const float *twc,
                                  float fx, float fy, float cx, float cy, float width, float height,
                                  const float *dloss_dus, const float *dloss_dcinv2ds, const float *dloss_dcolors,
-                                 const float *dloss_dalphas, int world, int rank, void *const *regions_host,
+                                 const float *dloss_dalphas, const float *moments, const float *cinv2ds,
+                                 float *dloss_dus_out, int world, int rank, void *const *regions_host,
                                  uint32_t epoch, gsb_stream_t stream) {
   GSB_REQUIRE(N >= 0, "preprocess_backward_push: N < 0");
   GSB_REQUIRE(world >= 1 && world <= kMaxWorld && rank >= 0 && rank < world && regions_host && epoch != 0,
               "preprocess_backward_push: bad world / rank / regions / epoch");
-  GSB_REQUIRE(N == 0 || (pws && rots && scales && shs && Rcw && tcw && twc && dloss_dus && dloss_dcinv2ds &&
-                         dloss_dcolors && dloss_dalphas),
-              "preprocess_backward_push: null pointer");
+  GSB_REQUIRE(N == 0 || (pws && rots && scales && shs && Rcw && tcw && twc), "preprocess_backward_push: null pointer");
+  GSB_REQUIRE(N == 0 || (moments ? (cinv2ds && dloss_dus_out)
+                                 : (dloss_dus && dloss_dcinv2ds && dloss_dcolors && dloss_dalphas)),
+              "preprocess_backward_push: null upstream gradient");
   const ExchangeGeom G = exchange_geom(N, sh_dim3, world);
   GradPush gp{};
   for (int p = 0; p < world; p++) {
@@ -477,8 +499,10 @@ int gsb_preprocess_backward_push(int N, int sh_dim3, const float *pws, const flo
   gp.world = world;
   gp.rank = rank;
   gp.epoch = epoch;
+  const MomentsIn mi{moments, cinv2ds, dloss_dus_out, nullptr};
   return launch_preprocess_bwd_push(N, sh_dim3, pws, rots, scales, shs, Rcw, tcw, twc, fx, fy, cx, cy, width, height,
-                                    dloss_dus, dloss_dcinv2ds, dloss_dcolors, gp, (cudaStream_t)stream);
+                                    dloss_dus, dloss_dcinv2ds, dloss_dcolors, gp, moments ? &mi : nullptr,
+                                    (cudaStream_t)stream);
 }
 
 int gsb_grad_reduce_broadcast(int N, int sh_dim3, int world, int rank, void *const *regions_host, uint32_t epoch,

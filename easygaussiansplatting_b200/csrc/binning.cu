@@ -137,8 +137,6 @@ __global__ void __launch_bounds__(256) k_ranges(int64_t P, const KeyT *__restric
 
 // Gathers the four per-Gaussian attribute arrays (all L2 resident: 36 B/Gaussian) into the
 // 48-B records the rasterizers gather with cp.async (gsid == nullptr: one record per Gaussian).
-// thr: the per-record bound of the warp-level culling test (common.cuh rec_can_touch); the
-// positive-definiteness check is done in fp64 so the determinant does not cancel.
 __global__ void __launch_bounds__(256) k_pack(int64_t P, const int32_t *__restrict__ gsid,
                                               const float2 *__restrict__ us,
                                               const float *__restrict__ cinv2ds,
@@ -148,28 +146,9 @@ __global__ void __launch_bounds__(256) k_pack(int64_t P, const int32_t *__restri
   if (p >= P) return;
   const int g = gsid != nullptr ? __ldg(gsid + p) : (int)p;  // nullptr: one record per Gaussian
   const float2 u = __ldg(us + g);
-  const float A = __ldg(cinv2ds + 3 * (size_t)g), B = __ldg(cinv2ds + 3 * (size_t)g + 1),
-              C = __ldg(cinv2ds + 3 * (size_t)g + 2);
-  const float al = __ldg(alphas + g);
-  // thr = log2(alpha / 0.002): -log2(g) <= thr is necessary for alpha' >= 0.002 (rec_can_touch).
-  float thr = INFINITY;  // never cull unless the conic is a proper positive definite form
-  if (al < ALPHA_SKIP) {
-    thr = -INFINITY;  // alpha * g < 0.002 everywhere: never contributes
-  } else {
-    // positive definite with a safety factor against fp32 cancellation in A C - B^2
-    const float ac = A * C;
-    const float det = fmaf(A, C, -B * B);
-    if (A > 0.f && C > 0.f && det > 1e-4f * ac && ac < 3.0e38f) {
-      const float t = __log2f(al * 500.0f) + 1e-4f;  // log2(alpha / 0.002), lg2.approx error << margin
-      if (t < 3.0e38f) thr = t;
-    }
-  }
-  Rec r;
-  r.q0 = make_float4(u.x, u.y, thr, 0.f);
-  r.q1 = make_float4(-0.5f * LOG2E * A, -LOG2E * B, -0.5f * LOG2E * C, al);
-  r.q2 = make_float4(__ldg(colors + 3 * (size_t)g), __ldg(colors + 3 * (size_t)g + 1),
-                     __ldg(colors + 3 * (size_t)g + 2), __int_as_float(g));
-  recs[p] = r;
+  recs[p] = build_record(u.x, u.y, __ldg(cinv2ds + 3 * (size_t)g), __ldg(cinv2ds + 3 * (size_t)g + 1),
+                         __ldg(cinv2ds + 3 * (size_t)g + 2), __ldg(alphas + g), __ldg(colors + 3 * (size_t)g),
+                         __ldg(colors + 3 * (size_t)g + 1), __ldg(colors + 3 * (size_t)g + 2), g);
 }
 
 // ---------------------------------------------------------------- phase 1
@@ -302,7 +281,7 @@ static int keys_sort_ranges(int N, int64_t P, const float *depths, const uint32_
 int launch_sort_and_pack(int H, int W, int N, int64_t P, uint32_t depth_key_max, const float *us,
                          const float *cinv2ds, const float *alphas, const float *depths, const float *colors,
                          const void *bin_ws, const BinLayout &BL, void *ws, const SortLayout &SL,
-                         int32_t *ranges, int32_t *gsid_per_patch, cudaStream_t st) {
+                         int32_t *ranges, int32_t *gsid_per_patch, bool pack, cudaStream_t st) {
   const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
   GSB_CUDA_TRY(cudaMemsetAsync(ranges, 0, sizeof(int32_t) * 2 * (size_t)gx * gy, st));
   if (P <= 0 || N <= 0) return 0;
@@ -313,7 +292,7 @@ int launch_sort_and_pack(int H, int W, int N, int64_t P, uint32_t depth_key_max,
   const KeyPlan kp = key_plan(H, W, depth_key_max);
   int rc = kp.narrow ? keys_sort_ranges<uint32_t>(N, P, depths, incl, rects, gx, kp, b, SL, ranges, gsid_per_patch, st)
                      : keys_sort_ranges<uint64_t>(N, P, depths, incl, rects, gx, kp, b, SL, ranges, gsid_per_patch, st);
-  if (rc) return rc;
+  if (rc || !pack) return rc;  // !pack: the caller already holds the per-Gaussian records
   return launch_pack_only(N, nullptr, us, cinv2ds, alphas, colors, reinterpret_cast<Rec *>(b + SL.recs), st);
 }
 

@@ -79,6 +79,30 @@ __device__ __forceinline__ bool rec_can_touch(const float4 &q0, const float4 &q1
   return !(qmin > q0.z + fmaf(2.0e-6f, S, 1.0e-5f));  // NaN anywhere keeps the record
 }
 
+// The 48-byte record the rasterizers work from (one per Gaussian).
+// thr = log2(alpha / 0.002): -log2(g) <= thr is necessary for alpha' >= 0.002 -- the bound of the
+// warp-level culling test (rec_can_touch); the positive-definiteness check carries a safety
+// factor against fp32 cancellation in A C - B^2.
+__device__ __forceinline__ Rec build_record(float ux, float uy, float A, float B, float C, float al, float cr,
+                                            float cg, float cb, int id) {
+  float thr = INFINITY;  // never cull unless the conic is a proper positive definite form
+  if (al < ALPHA_SKIP) {
+    thr = -INFINITY;  // alpha * g < 0.002 everywhere: never contributes
+  } else {
+    const float ac = A * C;
+    const float det = fmaf(A, C, -B * B);
+    if (A > 0.f && C > 0.f && det > 1e-4f * ac && ac < 3.0e38f) {
+      const float t = __log2f(al * 500.0f) + 1e-4f;  // log2(alpha / 0.002), lg2.approx error << margin
+      if (t < 3.0e38f) thr = t;
+    }
+  }
+  Rec r;
+  r.q0 = make_float4(ux, uy, thr, 0.f);
+  r.q1 = make_float4(-0.5f * LOG2E * A, -LOG2E * B, -0.5f * LOG2E * C, al);
+  r.q2 = make_float4(cr, cg, cb, __int_as_float(id));
+  return r;
+}
+
 // ---- system-scope flags for the multi-GPU gradient exchange (peer memory over NVLink)
 __device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");

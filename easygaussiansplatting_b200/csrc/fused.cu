@@ -49,7 +49,8 @@ __global__ void __launch_bounds__(PG) k_preprocess_fwd(
     const float *__restrict__ shs, const float *__restrict__ Rcw, const float *__restrict__ tcw,
     const float *__restrict__ twc, float fx, float fy, float cx, float cy, float tan_fovx, float tan_fovy,
     float *__restrict__ us, float *__restrict__ cinv2ds, float *__restrict__ colors,
-    float *__restrict__ depths, int32_t *__restrict__ areas) {
+    float *__restrict__ depths, int32_t *__restrict__ areas, const float *__restrict__ alphas,
+    Rec *__restrict__ recs) {
   constexpr int KS = 3 * K3;
   constexpr int SMF = TileT<KS>::FLOATS > TileT<4>::FLOATS ? TileT<KS>::FLOATS : TileT<4>::FLOATS;
   __shared__ float sm[SMF];
@@ -76,6 +77,9 @@ __global__ void __launch_bounds__(PG) k_preprocess_fwd(
     colors[3 * i] = col[0]; colors[3 * i + 1] = col[1]; colors[3 * i + 2] = col[2];
     *reinterpret_cast<int2 *>(areas + 2 * i) = make_int2(area[0], area[1]);
     depths[i] = depth;
+    // the rasterizers' per-Gaussian record, straight from registers (saves the k_pack pass)
+    if (recs != nullptr)
+      recs[i] = build_record(u[0], u[1], conic[0], conic[1], conic[2], __ldg(alphas + i), col[0], col[1], col[2], (int)i);
   }
 }
 
@@ -85,14 +89,19 @@ __global__ void __launch_bounds__(PG) k_preprocess_fwd(
 // overlaps the math of tile t+1), together with dL/dalpha from the rasterizer backward.  The
 // last CTA to finish raises this rank's arrival flag on every peer; k_grad_reduce_bcast
 // (comm.cu) then sums the slots of the rows it owns and broadcasts the result.
-template <int K3, bool PUSH>
+// MOM = the upstream gradients come as the rasterizer backward's raw moment rows [N,9] (see
+// raster_bwd.cu): the conversion k_finalize_grads would do (dL/du = -(A Sx + B Sy, B Sx + C Sy),
+// dL/dconic = (-Sxx/2, -Sxy, -Syy/2), dL/dcolor, dL/dalpha) happens here in registers, dL/du and
+// dL/dalpha are still written out (the caller's densification statistics / alpha gradient), and
+// the separate finalize pass with its 36 B/Gaussian round trip disappears.
+template <int K3, bool PUSH, bool MOM>
 __global__ void __launch_bounds__(PG) k_preprocess_bwd(
     int N, const float *__restrict__ pws, const float *__restrict__ rots, const float *__restrict__ scales,
     const float *__restrict__ shs, const float *__restrict__ Rcw, const float *__restrict__ tcw,
     const float *__restrict__ twc, float fx, float fy, float cx, float cy, float tan_fovx, float tan_fovy,
     const float *__restrict__ g_us, const float *__restrict__ g_cinv2ds, const float *__restrict__ g_colors,
     float *__restrict__ g_pws, float *__restrict__ g_shs, float *__restrict__ g_scales,
-    float *__restrict__ g_rots, GradPush gp) {
+    float *__restrict__ g_rots, GradPush gp, MomentsIn mi) {
   constexpr int KS = 3 * K3;
   constexpr int SMF = TileT<KS>::FLOATS > TileT<4>::FLOATS ? TileT<KS>::FLOATS : TileT<4>::FLOATS;
   __shared__ float sm[SMF];
@@ -104,7 +113,25 @@ __global__ void __launch_bounds__(PG) k_preprocess_bwd(
   float pw[3] = {0.f, 0.f, 1.f}, q[4] = {1.f, 0.f, 0.f, 0.f}, s[3] = {1.f, 1.f, 1.f};
   float gu[2] = {0.f, 0.f}, gci[3] = {0.f, 0.f, 0.f}, gcol[3] = {0.f, 0.f, 0.f};
   load_small_rows(pws, scales, rots, base + tid, valid, pw, s, q);  // see k_preprocess_fwd
-  if (valid) {
+  float galpha = 0.f;
+  if (MOM) {
+    if (valid) {
+      const long long i = base + tid;
+      float m[9];
+#pragma unroll
+      for (int k = 0; k < 9; k++) m[k] = __ldg(mi.moments + 9 * i + k);
+      const float A = __ldg(mi.cinv2ds + 3 * i), B = __ldg(mi.cinv2ds + 3 * i + 1), C = __ldg(mi.cinv2ds + 3 * i + 2);
+      // untouched Gaussians stay exactly 0 even if their conic is inf/NaN (k_finalize_grads)
+      const bool none = (m[0] == 0.f) && (m[1] == 0.f);
+      gu[0] = none ? 0.f : -(A * m[0] + B * m[1]);
+      gu[1] = none ? 0.f : -(B * m[0] + C * m[1]);
+      gci[0] = -0.5f * m[2]; gci[1] = -m[3]; gci[2] = -0.5f * m[4];
+      gcol[0] = m[6]; gcol[1] = m[7]; gcol[2] = m[8];
+      galpha = m[5];
+      *reinterpret_cast<float2 *>(mi.dus_out + 2 * i) = make_float2(gu[0], gu[1]);
+      if (mi.dalphas_out != nullptr) mi.dalphas_out[i] = galpha;
+    }
+  } else if (valid) {
     const long long i = base + tid;
     const float2 g2 = __ldg(reinterpret_cast<const float2 *>(g_us) + i);
     gu[0] = g2.x; gu[1] = g2.y;
@@ -128,7 +155,7 @@ __global__ void __launch_bounds__(PG) k_preprocess_bwd(
     g_rots = sb + gp.off_rots;
     g_pws = sb + gp.off_pws;
     g_scales = sb + gp.off_scales;
-    if (valid) (sb + gp.off_alphas)[drow + tid] = __ldg(gp.g_alphas + base + tid);
+    if (valid) (sb + gp.off_alphas)[drow + tid] = MOM ? galpha : __ldg(gp.g_alphas + base + tid);
   }
   tile_flush<KS>(g_shs, drow, nv, sm, tid);
   if (valid) {  // the 10 small gradient floats: direct strided stores (no staging, no barriers)
@@ -167,13 +194,15 @@ __global__ void __launch_bounds__(PG) k_preprocess_bwd(
 int launch_preprocess_fwd(int N, int k3, const float *pws, const float *rots, const float *scales,
                           const float *shs, const float *Rcw, const float *tcw, const float *twc, float fx,
                           float fy, float cx, float cy, float width, float height, float *us, float *cinv2ds,
-                          float *colors, float *depths, int32_t *areas, cudaStream_t st) {
+                          float *colors, float *depths, int32_t *areas, const float *alphas, Rec *recs,
+                          cudaStream_t st) {
   if (N <= 0) return 0;
   const float tfx = width / (2 * fx), tfy = height / (2 * fy);
   const int nb = (N + PG - 1) / PG;
   ProfScope ps(K_PRE_FWD, st);
   GSB_DISPATCH_K3(k3, (k_preprocess_fwd<K3><<<nb, PG, 0, st>>>(N, pws, rots, scales, shs, Rcw, tcw, twc, fx, fy, cx,
-                                                                cy, tfx, tfy, us, cinv2ds, colors, depths, areas)));
+                                                                cy, tfx, tfy, us, cinv2ds, colors, depths, areas,
+                                                                alphas, recs)));
   GSB_CUDA_TRY(cudaGetLastError());
   return 0;
 }
@@ -182,15 +211,20 @@ int launch_preprocess_bwd(int N, int k3, const float *pws, const float *rots, co
                           const float *shs, const float *Rcw, const float *tcw, const float *twc, float fx,
                           float fy, float cx, float cy, float width, float height, const float *g_us,
                           const float *g_cinv2ds, const float *g_colors, float *g_pws, float *g_shs,
-                          float *g_scales, float *g_rots, cudaStream_t st) {
+                          float *g_scales, float *g_rots, const MomentsIn *mi, cudaStream_t st) {
   if (N <= 0) return 0;
   const float tfx = width / (2 * fx), tfy = height / (2 * fy);
   const int nb = (N + PG - 1) / PG;
   ProfScope ps(K_PRE_BWD, st);
-  GSB_DISPATCH_K3(k3, (k_preprocess_bwd<K3, false><<<nb, PG, 0, st>>>(N, pws, rots, scales, shs, Rcw, tcw, twc, fx,
-                                                                       fy, cx, cy, tfx, tfy, g_us, g_cinv2ds,
-                                                                       g_colors, g_pws, g_shs, g_scales, g_rots,
-                                                                       GradPush{})));
+  if (mi != nullptr) {
+    GSB_DISPATCH_K3(k3, (k_preprocess_bwd<K3, false, true><<<nb, PG, 0, st>>>(
+                            N, pws, rots, scales, shs, Rcw, tcw, twc, fx, fy, cx, cy, tfx, tfy, nullptr, nullptr, nullptr,
+                            g_pws, g_shs, g_scales, g_rots, GradPush{}, *mi)));
+  } else {
+    GSB_DISPATCH_K3(k3, (k_preprocess_bwd<K3, false, false><<<nb, PG, 0, st>>>(
+                            N, pws, rots, scales, shs, Rcw, tcw, twc, fx, fy, cx, cy, tfx, tfy, g_us, g_cinv2ds, g_colors,
+                            g_pws, g_shs, g_scales, g_rots, GradPush{}, MomentsIn{})));
+  }
   GSB_CUDA_TRY(cudaGetLastError());
   return 0;
 }
@@ -198,14 +232,21 @@ int launch_preprocess_bwd(int N, int k3, const float *pws, const float *rots, co
 int launch_preprocess_bwd_push(int N, int k3, const float *pws, const float *rots, const float *scales,
                                const float *shs, const float *Rcw, const float *tcw, const float *twc, float fx,
                                float fy, float cx, float cy, float width, float height, const float *g_us,
-                               const float *g_cinv2ds, const float *g_colors, const GradPush &gp, cudaStream_t st) {
+                               const float *g_cinv2ds, const float *g_colors, const GradPush &gp,
+                               const MomentsIn *mi, cudaStream_t st) {
   if (N <= 0) return 0;
   const float tfx = width / (2 * fx), tfy = height / (2 * fy);
   const int nb = (N + PG - 1) / PG;
   ProfScope ps(K_PRE_BWD, st);
-  GSB_DISPATCH_K3(k3, (k_preprocess_bwd<K3, true><<<nb, PG, 0, st>>>(N, pws, rots, scales, shs, Rcw, tcw, twc, fx, fy,
-                                                                      cx, cy, tfx, tfy, g_us, g_cinv2ds, g_colors,
-                                                                      nullptr, nullptr, nullptr, nullptr, gp)));
+  if (mi != nullptr) {
+    GSB_DISPATCH_K3(k3, (k_preprocess_bwd<K3, true, true><<<nb, PG, 0, st>>>(
+                            N, pws, rots, scales, shs, Rcw, tcw, twc, fx, fy, cx, cy, tfx, tfy, nullptr, nullptr, nullptr,
+                            nullptr, nullptr, nullptr, nullptr, gp, *mi)));
+  } else {
+    GSB_DISPATCH_K3(k3, (k_preprocess_bwd<K3, true, false><<<nb, PG, 0, st>>>(
+                            N, pws, rots, scales, shs, Rcw, tcw, twc, fx, fy, cx, cy, tfx, tfy, g_us, g_cinv2ds, g_colors,
+                            nullptr, nullptr, nullptr, nullptr, gp, MomentsIn{})));
+  }
   GSB_CUDA_TRY(cudaGetLastError());
   return 0;
 }

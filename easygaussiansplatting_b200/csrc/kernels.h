@@ -42,12 +42,20 @@ int launch_inv_cov2d(int N, const float *cov2ds, float *depths, float *cinv2ds, 
 int launch_preprocess_fwd(int N, int k3, const float *pws, const float *rots, const float *scales,
                           const float *shs, const float *Rcw, const float *tcw, const float *twc, float fx,
                           float fy, float cx, float cy, float width, float height, float *us, float *cinv2ds,
-                          float *colors, float *depths, int32_t *areas, cudaStream_t st);
+                          float *colors, float *depths, int32_t *areas, const float *alphas, Rec *recs,
+                          cudaStream_t st);
+// upstream gradients given as the rasterizer backward's moment rows (fused.cu, MOM variants)
+struct MomentsIn {
+  const float *moments;  // [N,9]
+  const float *cinv2ds;  // [N,3]
+  float *dus_out;        // [N,2]  dL/du, still needed by the caller
+  float *dalphas_out;    // [N]    dL/dalpha (nullable: the push variant forwards it instead)
+};
 int launch_preprocess_bwd(int N, int k3, const float *pws, const float *rots, const float *scales,
                           const float *shs, const float *Rcw, const float *tcw, const float *twc, float fx,
                           float fy, float cx, float cy, float width, float height, const float *g_us,
                           const float *g_cinv2ds, const float *g_colors, float *g_pws, float *g_shs,
-                          float *g_scales, float *g_rots, cudaStream_t st);
+                          float *g_scales, float *g_rots, const MomentsIn *mi, cudaStream_t st);
 
 // ---- multi-GPU gradient exchange (comm.cu; the producer is the PUSH variant in fused.cu).
 // Every rank owns one region of peer-mapped memory:
@@ -79,7 +87,8 @@ struct GradPush {
 int launch_preprocess_bwd_push(int N, int k3, const float *pws, const float *rots, const float *scales,
                                const float *shs, const float *Rcw, const float *tcw, const float *twc, float fx,
                                float fy, float cx, float cy, float width, float height, const float *g_us,
-                               const float *g_cinv2ds, const float *g_colors, const GradPush &gp, cudaStream_t st);
+                               const float *g_cinv2ds, const float *g_colors, const GradPush &gp,
+                               const MomentsIn *mi, cudaStream_t st);
 int launch_grad_reduce_bcast(const ExchangeGeom &G, int rank, void *const *regions, uint32_t epoch,
                              cudaStream_t st);
 
@@ -125,7 +134,7 @@ int sort_layout(int N, int H, int W, int64_t P, SortLayout *out);
 int launch_sort_and_pack(int H, int W, int N, int64_t P, uint32_t depth_key_max, const float *us,
                          const float *cinv2ds, const float *alphas, const float *depths, const float *colors,
                          const void *bin_ws, const BinLayout &BL, void *ws, const SortLayout &SL,
-                         int32_t *ranges, int32_t *gsid_per_patch, cudaStream_t st);
+                         int32_t *ranges, int32_t *gsid_per_patch, bool pack, cudaStream_t st);
 int launch_pack_only(int64_t P, const int32_t *gsid_per_patch, const float *us, const float *cinv2ds,
                      const float *alphas, const float *colors, Rec *recs, cudaStream_t st);
 
@@ -140,6 +149,6 @@ int launch_draw_backward(int H, int W, int N, const int32_t *ranges, const Rec *
                          const int32_t *contrib,
                          const float *final_tau, const float *dloss_dgammas, const float *cinv2ds,
                          float *moments, int *tile_counter, float *dloss_dus, float *dloss_dcinv2ds,
-                         float *dloss_dalphas, float *dloss_dcolors, cudaStream_t st);
+                         float *dloss_dalphas, float *dloss_dcolors, bool finalize, cudaStream_t st);
 
 }  // namespace gsb

@@ -70,7 +70,7 @@ int launch_draw_backward(int H, int W, int N, const int32_t *ranges, const Rec *
                          const int32_t *contrib,
                          const float *final_tau, const float *dloss_dgammas, const float *cinv2ds,
                          float *moments, int *tile_counter, float *dloss_dus, float *dloss_dcinv2ds,
-                         float *dloss_dalphas, float *dloss_dcolors, cudaStream_t st) {
+                         float *dloss_dalphas, float *dloss_dcolors, bool finalize, cudaStream_t st) {
   const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
   if (gx <= 0 || gy <= 0 || N <= 0) return 0;
   GSB_CUDA_TRY(cudaMemsetAsync(moments, 0, sizeof(float) * MOM * (size_t)N, st));
@@ -80,7 +80,7 @@ int launch_draw_backward(int H, int W, int N, const int32_t *ranges, const Rec *
     if (rc) return rc;
   }
   GSB_CUDA_TRY(cudaGetLastError());
-  {
+  if (finalize) {  // otherwise the caller consumes the moment rows (gsb_preprocess_backward)
     ProfScope ps(K_FINALIZE, st);
     k_finalize_grads<<<(N + PG - 1) / PG, PG, 0, st>>>(N, moments, cinv2ds, dloss_dus, dloss_dcinv2ds,
                                                        dloss_dalphas, dloss_dcolors);

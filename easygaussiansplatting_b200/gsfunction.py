@@ -99,11 +99,12 @@ class GSFunctionFused(torch.autograd.Function):
     @staticmethod
     def forward(ctx, pws, shs, alphas, scales, rots, us, cam):
         from . import ops
-        us, cinv2ds, colors, depths, areas = ops.preprocess(
+        # the per-Gaussian records of the rasterizers come straight out of the fused forward
+        us, cinv2ds, colors, depths, areas, records = ops.preprocess(
             pws, rots, scales, shs, cam.Rcw, cam.tcw, cam.twc, cam.fx, cam.fy, cam.cx, cam.cy,
-            cam.width, cam.height)
+            cam.width, cam.height, alphas=alphas)
         image, contrib, final_tau, patch_range_per_tile, gsid_per_patch = ops.splat(
-            cam.height, cam.width, us, cinv2ds, alphas, depths, colors, areas)
+            cam.height, cam.width, us, cinv2ds, alphas, depths, colors, areas, records=records)
         ctx.cam = cam
         ctx.alpha_shape = alphas.shape
         ctx.save_for_backward(pws, shs, alphas, scales, rots, us, cinv2ds, depths, colors, contrib,
@@ -116,19 +117,19 @@ class GSFunctionFused(torch.autograd.Function):
         cam = ctx.cam
         (pws, shs, alphas, scales, rots, us, cinv2ds, depths, colors, contrib, final_tau,
          patch_range_per_tile, gsid_per_patch) = ctx.saved_tensors
-        dloss_dus, dloss_dcinv2ds, dloss_dalphas, dloss_dcolors = ops.splatB(
-            cam.height, cam.width, us, cinv2ds, alphas, depths, colors, contrib, final_tau,
-            patch_range_per_tile, gsid_per_patch, dloss_dgammas)
+        # the rasterizer backward leaves its raw moment rows; the fused per-Gaussian backward
+        # converts them in registers (no finalize pass, no 32 B/Gaussian round trip)
+        moments = ops.splatB(cam.height, cam.width, us, cinv2ds, alphas, depths, colors, contrib, final_tau,
+                             patch_range_per_tile, gsid_per_patch, dloss_dgammas, moments_only=True)
         ex = getattr(cam, "grad_exchange", None)
         if ex is not None:
             # multi-view data parallel (parallel.GradExchange): the per-Gaussian backward pushes
             # its tiles into peer memory and the gradients come back already summed over ranks
             # (dloss_dus stays this view's own: it only feeds the densification statistics)
-            g = ex.backward(pws, rots, scales, shs, cam, dloss_dus, dloss_dcinv2ds, dloss_dcolors, dloss_dalphas)
+            g = ex.backward(pws, rots, scales, shs, cam, moments=moments, cinv2ds=cinv2ds)
             return (g["dpws"], g["dshs"], g["dalphas"].reshape(ctx.alpha_shape), g["dscales"], g["drots"],
-                    dloss_dus.squeeze(1), None)
-        dpws, dshs, dscales, drots = ops.preprocessB(
+                    g["dus"], None)
+        dpws, dshs, dscales, drots, dloss_dus, dloss_dalphas = ops.preprocessB(
             pws, rots, scales, shs, cam.Rcw, cam.tcw, cam.twc, cam.fx, cam.fy, cam.cx, cam.cy,
-            cam.width, cam.height, dloss_dus, dloss_dcinv2ds, dloss_dcolors)
-        return (dpws, dshs, dloss_dalphas.reshape(ctx.alpha_shape), dscales, drots,
-                dloss_dus.squeeze(1), None)
+            cam.width, cam.height, None, None, None, moments=moments, cinv2ds=cinv2ds)
+        return (dpws, dshs, dloss_dalphas.reshape(ctx.alpha_shape), dscales, drots, dloss_dus, None)

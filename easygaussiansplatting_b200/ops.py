@@ -155,10 +155,12 @@ def inverseCov2D(cov2ds, depths, calc_J):
     return [cinv, areas, _jac(J)] if calc_J else [cinv, areas]
 
 
-def splat(height, width, us, cinv2ds, alphas, depths, colors, areas):
+def splat(height, width, us, cinv2ds, alphas, depths, colors, areas, records=None):
     """ext.cpp:10-18.  MUTATES depths / areas for Gaussians that touch no tile
     (kernel.cu:114-119).  -> [image[3,H,W], contrib[H,W] i32, final_tau[H,W],
-    patch_range_per_tile[T,2] i32, gsid_per_patch[P] i32]"""
+    patch_range_per_tile[T,2] i32, gsid_per_patch[P] i32]
+    records (extension): the packed per-Gaussian records `preprocess(..., alphas=...)` wrote;
+    the pack pass is then skipped."""
     H, W = int(height), int(width)
     if H <= 0 or W <= 0:
         raise ValueError("height and width must be positive")
@@ -189,19 +191,26 @@ def splat(height, width, us, cinv2ds, alphas, depths, colors, areas):
         final_tau = torch.empty((H, W), dtype=torch.float32, device=dev)
         ranges = torch.empty((T, 2), dtype=torch.int32, device=dev)
         gsid = torch.empty((P,), dtype=torch.int32, device=dev)
+        if records is not None:
+            records = _chk(records, "records", last=12, ndim=2)
+            if records.shape[0] != N:
+                raise ValueError("records must be [N, 12]")
         _lib.check(lib.gsb_splat_render(H, W, N, P, dkmax.value, _ptr(us), _ptr(cinv2ds), _ptr(alphas),
-                                        _ptr(depths), _ptr(colors), _ptr(bin_ws), _ptr(ws), ws_bytes,
+                                        _ptr(depths), _ptr(colors), _ptr(records), _ptr(bin_ws), _ptr(ws), ws_bytes,
                                         _ptr(image), _ptr(contrib), _ptr(final_tau), _ptr(ranges), _ptr(gsid),
                                         st), lib)
         # the workspaces are consumed by kernels already enqueued on `st`; the caching
         # allocator only reuses them for later work on the same stream
         if P > 0:
-            _remember_records(gsid, ws, lib.gsb_splat_records_offset(N, H, W, P), (us, cinv2ds, alphas, colors))
+            if records is not None:
+                _remember_records(gsid, records, 0, (us, cinv2ds, alphas, colors))
+            else:
+                _remember_records(gsid, ws, lib.gsb_splat_records_offset(N, H, W, P), (us, cinv2ds, alphas, colors))
     return [image, contrib, final_tau, ranges, gsid]
 
 
-# The forward leaves the packed, sorted record stream in its workspace; splatB can reuse it
-# instead of gathering the same records again, provided it is called with the very tensors the
+# The forward leaves the packed per-Gaussian records in its workspace (or got them from
+# `preprocess`); splatB can reuse them instead of packing the same records again, provided it is called with the very tensors the
 # forward saw, unmodified (checked through data_ptr + torch's in-place version counter).
 _RECORD_CACHE = []  # [(gsid_ptr, P, ws, offset, ((ptr, version), ...))], newest first, <= 2 entries
 
@@ -237,9 +246,11 @@ def clear_record_cache():
 
 
 def splatB(height, width, us, cinv2ds, alphas, depths, colors, contrib, final_tau,
-           patch_range_per_tile, gsid_per_patch, dloss_dgammas):
+           patch_range_per_tile, gsid_per_patch, dloss_dgammas, moments_only=False):
     """ext.cpp:20-32.  -> [dloss_dus[N,1,2], dloss_dcinv2ds[N,1,3], dloss_dalphas[N,1,1],
-    dloss_dcolors[N,1,3]]   (`depths` is accepted and unused, as in the reference)"""
+    dloss_dcolors[N,1,3]]   (`depths` is accepted and unused, as in the reference)
+    moments_only (extension): -> the raw moment rows [N,9] for `preprocessB(..., moments=...)`;
+    the conversion pass to the four tensors is skipped."""
     H, W = int(height), int(width)
     us = _chk(us, "us", last=2, ndim=2); cinv2ds = _chk(cinv2ds, "cinv2ds", last=3, ndim=2)
     alphas = _chk(alphas, "alphas"); colors = _chk(colors, "colors", last=3, ndim=2)
@@ -259,8 +270,13 @@ def splatB(height, width, us, cinv2ds, alphas, depths, colors, contrib, final_ta
     P = gsid.numel()
     dev = us.device
     o = dict(dtype=torch.float32, device=dev)
-    du = torch.empty((N, 1, 2), **o); dc = torch.empty((N, 1, 3), **o)
-    da = torch.empty((N, 1, 1), **o); dcol = torch.empty((N, 1, 3), **o)
+    if moments_only:
+        du = dc = da = dcol = None
+        moments = torch.empty((N, 9), **o)
+    else:
+        du = torch.empty((N, 1, 2), **o); dc = torch.empty((N, 1, 3), **o)
+        da = torch.empty((N, 1, 1), **o); dcol = torch.empty((N, 1, 3), **o)
+        moments = None
     lib = _L()
     with torch.cuda.device(dev):
         recs = _cached_records(gsid, (us, cinv2ds, alphas, colors)) if P > 0 else None
@@ -270,17 +286,21 @@ def splatB(height, width, us, cinv2ds, alphas, depths, colors, contrib, final_ta
         _lib.check(lib.gsb_splat_backward(H, W, N, P, _ptr(us), _ptr(cinv2ds), _ptr(alphas), _ptr(colors),
                                           _ptr(contrib), _ptr(final_tau), _ptr(ranges), _ptr(gsid), _ptr(dl),
                                           recs, _ptr(ws), ws_bytes, _ptr(du), _ptr(dc), _ptr(da), _ptr(dcol),
-                                          _stream()), lib)
+                                          _ptr(moments), _stream()), lib)
+    if moments_only:
+        return moments
     # tagged so that the reference's `dloss_d* @ jacobian` chain takes the streaming matmul
     return [_jac(du), _jac(dc), _jac(da), _jac(dcol)]
 
 
 # ---------------------------------------------------------------------------------------
 # Extensions (not in the reference module): the fused per-Gaussian path, SURVEY 8f row N1.
-def preprocess(pws, rots, scales, shs, Rcw, tcw, twc, focal_x, focal_y, center_x, center_y, width, height):
+def preprocess(pws, rots, scales, shs, Rcw, tcw, twc, focal_x, focal_y, center_x, center_y, width, height,
+               alphas=None):
     """project + computeCov3D + computeCov2D + sh2Color + inverseCov2D (calc_J=False) in one
     kernel.  -> [us[N,2], cinv2ds[N,3], colors[N,3], depths[N], areas[N,2] int32], ready for
-    `splat`."""
+    `splat`.  With alphas[N] a sixth output: the packed per-Gaussian records [N,12] for
+    `splat(..., records=...)`."""
     pws = _chk(pws, "pws", last=3, ndim=2); rots = _chk(rots, "rots", last=4, ndim=2)
     scales = _chk(scales, "scales", last=3, ndim=2); shs = _chk(shs, "shs", ndim=2)
     Rcw = _chk(Rcw, "Rcw"); tcw = _chk(tcw, "tcw"); twc = _chk(twc, "twc")
@@ -296,28 +316,45 @@ def preprocess(pws, rots, scales, shs, Rcw, tcw, twc, focal_x, focal_y, center_x
     o = dict(dtype=torch.float32, device=pws.device)
     us = torch.empty((N, 2), **o); cinv = torch.empty((N, 3), **o); col = torch.empty((N, 3), **o)
     depths = torch.empty((N,), **o); areas = torch.empty((N, 2), dtype=torch.int32, device=pws.device)
+    records = None
+    if alphas is not None:
+        alphas = _chk(alphas, "alphas")
+        if alphas.numel() != N:
+            raise ValueError("alphas must have N elements")
+        records = torch.empty((N, 12), **o)
     lib = _L()
     with torch.cuda.device(pws.device):
         _lib.check(lib.gsb_preprocess_forward(
             N, k, _ptr(pws), _ptr(rots), _ptr(scales), _ptr(shs), _ptr(Rcw), _ptr(tcw), _ptr(twc),
             float(focal_x), float(focal_y), float(center_x), float(center_y), float(width), float(height),
-            _ptr(us), _ptr(cinv), _ptr(col), _ptr(depths), _ptr(areas), _stream()), lib)
-    return [us, cinv, col, depths, areas]
+            _ptr(us), _ptr(cinv), _ptr(col), _ptr(depths), _ptr(areas), _ptr(alphas), _ptr(records), _stream()), lib)
+    return [us, cinv, col, depths, areas] + ([records] if records is not None else [])
 
 
 def preprocessB(pws, rots, scales, shs, Rcw, tcw, twc, focal_x, focal_y, center_x, center_y, width, height,
-                dloss_dus, dloss_dcinv2ds, dloss_dcolors):
+                dloss_dus, dloss_dcinv2ds, dloss_dcolors, moments=None, cinv2ds=None):
     """Vector-Jacobian products of the five per-Gaussian stages (== the torch.bmm chain of
-    gsmodel.py:72-85).  -> [dloss_dpws[N,3], dloss_dshs[N,3k], dloss_dscales[N,3], dloss_drots[N,4]]"""
+    gsmodel.py:72-85).  -> [dloss_dpws[N,3], dloss_dshs[N,3k], dloss_dscales[N,3], dloss_drots[N,4]]
+    With moments[N,9] (from `splatB(..., moments_only=True)`) and the forward's cinv2ds[N,3] the
+    three dloss_d* arguments are ignored (pass None) and two more outputs follow:
+    dloss_dus[N,2], dloss_dalphas[N]."""
     pws = _chk(pws, "pws", last=3, ndim=2); rots = _chk(rots, "rots", last=4, ndim=2)
     scales = _chk(scales, "scales", last=3, ndim=2); shs = _chk(shs, "shs", ndim=2)
     Rcw = _chk(Rcw, "Rcw"); tcw = _chk(tcw, "tcw"); twc = _chk(twc, "twc")
-    gu = _chk(dloss_dus, "dloss_dus", last=2); gc = _chk(dloss_dcinv2ds, "dloss_dcinv2ds", last=3)
-    gcol = _chk(dloss_dcolors, "dloss_dcolors", last=3)
-    _same_device(pws, rots, scales, shs, Rcw, tcw, twc, gu, gc, gcol)
     N = pws.shape[0]
-    if not (rots.shape[0] == N and scales.shape[0] == N and shs.shape[0] == N and gu.numel() == 2 * N
-            and gc.numel() == 3 * N and gcol.numel() == 3 * N):
+    if moments is not None:
+        moments = _chk(moments, "moments", last=9, ndim=2); cinv2ds = _chk(cinv2ds, "cinv2ds", last=3, ndim=2)
+        _same_device(pws, rots, scales, shs, Rcw, tcw, twc, moments, cinv2ds)
+        if moments.shape[0] != N or cinv2ds.shape[0] != N:
+            raise ValueError("moments / cinv2ds must have N rows")
+        gu = gc = gcol = None
+    else:
+        gu = _chk(dloss_dus, "dloss_dus", last=2); gc = _chk(dloss_dcinv2ds, "dloss_dcinv2ds", last=3)
+        gcol = _chk(dloss_dcolors, "dloss_dcolors", last=3)
+        _same_device(pws, rots, scales, shs, Rcw, tcw, twc, gu, gc, gcol)
+        if not (gu.numel() == 2 * N and gc.numel() == 3 * N and gcol.numel() == 3 * N):
+            raise ValueError("preprocessB inputs disagree on N")
+    if not (rots.shape[0] == N and scales.shape[0] == N and shs.shape[0] == N):
         raise ValueError("preprocessB inputs disagree on N")
     if shs.shape[1] % 3 != 0 or shs.shape[1] // 3 not in (1, 4, 9, 16):
         raise ValueError("shs must be [N, 3k] with k in {1,4,9,16}, got %s" % (tuple(shs.shape),))
@@ -332,10 +369,13 @@ def preprocessB(pws, rots, scales, shs, Rcw, tcw, twc, focal_x, focal_y, center_
     gq = bucket[N * 3 * k:N * (3 * k + 4)].view(N, 4)
     gpw = bucket[N * (3 * k + 4):N * (3 * k + 7)].view(N, 3)
     gs = bucket[N * (3 * k + 7):].view(N, 3)
+    dus = torch.empty((N, 2), **o) if moments is not None else None
+    dal = torch.empty((N,), **o) if moments is not None else None
     lib = _L()
     with torch.cuda.device(pws.device):
         _lib.check(lib.gsb_preprocess_backward(
             N, k, _ptr(pws), _ptr(rots), _ptr(scales), _ptr(shs), _ptr(Rcw), _ptr(tcw), _ptr(twc),
             float(focal_x), float(focal_y), float(center_x), float(center_y), float(width), float(height),
-            _ptr(gu), _ptr(gc), _ptr(gcol), _ptr(gpw), _ptr(gsh), _ptr(gs), _ptr(gq), _stream()), lib)
-    return [gpw, gsh, gs, gq]
+            _ptr(gu), _ptr(gc), _ptr(gcol), _ptr(gpw), _ptr(gsh), _ptr(gs), _ptr(gq), _ptr(moments), _ptr(cinv2ds),
+            _ptr(dus), _ptr(dal), _stream()), lib)
+    return [gpw, gsh, gs, gq] + ([dus, dal] if moments is not None else [])

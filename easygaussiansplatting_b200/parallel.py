@@ -100,8 +100,8 @@ class GradExchange:
 
         ex = GradExchange.from_process_group(N, sh_dim3, device)      # once; collective
         ...
-        grads = ex.backward(pws, rots, scales, shs, cam, dloss_dus, dloss_dcinv2ds, dloss_dcolors,
-                            dloss_dalphas)        # dict dpws dshs dscales drots dalphas, already summed
+        grads = ex.backward(pws, rots, scales, shs, cam, moments=moments, cinv2ds=cinv2ds)
+                                                  # dict dpws dshs dscales drots dalphas, already summed
 
     The returned tensors are views of this rank's result region and are overwritten by the next
     call.  `regions` (low-level constructor): device pointers of every rank's region as seen
@@ -162,24 +162,39 @@ class GradExchange:
             dist.barrier(group=group)
         return cls(N, sh_dim3, world, rank, regions, device, own_region=own, peers=peers)
 
-    def push(self, pws, rots, scales, shs, cam, dloss_dus, dloss_dcinv2ds, dloss_dcolors, dloss_dalphas):
-        """phase 1: the fused per-Gaussian backward, storing into the owners' staging slots"""
+    def push(self, pws, rots, scales, shs, cam, dloss_dus=None, dloss_dcinv2ds=None, dloss_dcolors=None,
+             dloss_dalphas=None, moments=None, cinv2ds=None):
+        """phase 1: the fused per-Gaussian backward, storing into the owners' staging slots.
+        Upstream gradients: the four dloss_d* tensors of `splatB`, or moments[N,9] (from
+        `splatB(..., moments_only=True)`) + the forward's cinv2ds -- then this view's own
+        dloss_dus[N,2] is returned (it is not part of the exchange)."""
         from . import _lib
         from .ops import _chk, _ptr, _stream
         pws = _chk(pws, "pws", last=3, ndim=2); rots = _chk(rots, "rots", last=4, ndim=2)
         scales = _chk(scales, "scales", last=3, ndim=2); shs = _chk(shs, "shs", ndim=2)
-        gu = _chk(dloss_dus, "dloss_dus", last=2); gc = _chk(dloss_dcinv2ds, "dloss_dcinv2ds", last=3)
-        gcol = _chk(dloss_dcolors, "dloss_dcolors", last=3); ga = _chk(dloss_dalphas, "dloss_dalphas")
         N = pws.shape[0]
-        if N != self.N or shs.shape[1] != 3 * self.k3 or ga.numel() != N or gu.numel() != 2 * N:
+        if N != self.N or shs.shape[1] != 3 * self.k3:
             raise ValueError("GradExchange was built for N=%d, sh_dim3=%d" % (self.N, self.k3))
+        gu = gc = gcol = ga = dus = None
+        if moments is not None:
+            moments = _chk(moments, "moments", last=9, ndim=2); cinv2ds = _chk(cinv2ds, "cinv2ds", last=3, ndim=2)
+            if moments.shape[0] != N or cinv2ds.shape[0] != N:
+                raise ValueError("moments / cinv2ds must have N rows")
+            dus = torch.empty((N, 2), dtype=torch.float32, device=pws.device)
+        else:
+            gu = _chk(dloss_dus, "dloss_dus", last=2); gc = _chk(dloss_dcinv2ds, "dloss_dcinv2ds", last=3)
+            gcol = _chk(dloss_dcolors, "dloss_dcolors", last=3); ga = _chk(dloss_dalphas, "dloss_dalphas")
+            if ga.numel() != N or gu.numel() != 2 * N:
+                raise ValueError("upstream gradients disagree on N")
         self.epoch += 1
         with torch.cuda.device(pws.device):
             _lib.check(self.lib.gsb_preprocess_backward_push(
                 N, self.k3, _ptr(pws), _ptr(rots), _ptr(scales), _ptr(shs), _ptr(_chk(cam.Rcw, "Rcw")),
                 _ptr(_chk(cam.tcw, "tcw")), _ptr(_chk(cam.twc, "twc")), float(cam.fx), float(cam.fy), float(cam.cx),
                 float(cam.cy), float(cam.width), float(cam.height), _ptr(gu), _ptr(gc), _ptr(gcol), _ptr(ga),
-                self.world, self.rank, self.regions, self.epoch, _stream()), self.lib)
+                _ptr(moments), _ptr(cinv2ds), _ptr(dus), self.world, self.rank, self.regions, self.epoch, _stream()),
+                self.lib)
+        return dus
 
     def reduce(self):
         """phase 2: sum the slots of the owned rows, broadcast, wait for the peers' slices"""
@@ -190,9 +205,16 @@ class GradExchange:
                                                           self.epoch, _stream()), self.lib)
         return self._views
 
-    def backward(self, pws, rots, scales, shs, cam, dloss_dus, dloss_dcinv2ds, dloss_dcolors, dloss_dalphas):
-        self.push(pws, rots, scales, shs, cam, dloss_dus, dloss_dcinv2ds, dloss_dcolors, dloss_dalphas)
-        return self.reduce()
+    def backward(self, pws, rots, scales, shs, cam, dloss_dus=None, dloss_dcinv2ds=None, dloss_dcolors=None,
+                 dloss_dalphas=None, moments=None, cinv2ds=None):
+        """push + reduce; -> dict dpws dshs dscales drots dalphas (summed over ranks) and, with
+        moments, `dus` (this view's own dL/du)"""
+        dus = self.push(pws, rots, scales, shs, cam, dloss_dus, dloss_dcinv2ds, dloss_dcolors, dloss_dalphas,
+                        moments=moments, cinv2ds=cinv2ds)
+        out = dict(self.reduce())
+        if dus is not None:
+            out["dus"] = dus
+        return out
 
     def status(self):
         """0 = fine; 1 = a flag wait timed out (a peer never arrived) -- results invalid"""

@@ -85,16 +85,27 @@ int gsb_inverse_cov2d(int N, const float *cov2ds, float *depths, float *cinv2ds,
  * width/height feed the fov clamp exactly as in gsb_compute_cov2d.  Outputs of the forward
  * feed gsb_splat_bin / gsb_splat_render unchanged; the backward consumes gsb_splat_backward's
  * dloss_dus / dloss_dcinv2ds / dloss_dcolors (dloss_dalphas passes through untouched) and
- * writes dloss_dpws[N,3], dloss_dshs[N,3k], dloss_dscales[N,3], dloss_drots[N,4]. */
+ * writes dloss_dpws[N,3], dloss_dshs[N,3k], dloss_dscales[N,3], dloss_drots[N,4].
+ * Two optional short cuts around passes that only re-format data:
+ *   forward:  alphas[N] + records (both or neither) -- also writes the N packed 48-byte
+ *             per-Gaussian records the rasterizers gather from; hand them to gsb_splat_render /
+ *             gsb_splat_backward as `packed_records` and the separate pack pass is skipped;
+ *   backward: moments[N,9] + cinv2ds[N,3] + dloss_dus_out[N,2] + dloss_dalphas_out[N] (all or
+ *             none) -- the upstream gradients are taken as the raw moment rows
+ *             gsb_splat_backward leaves in `moments_out`; the three dloss_d* inputs are then
+ *             ignored (may be NULL) and dL/du, dL/dalpha are written to the two outputs. */
 int gsb_preprocess_forward(int N, int sh_dim3, const float *pws, const float *rots, const float *scales,
                            const float *shs, const float *Rcw, const float *tcw, const float *twc, float fx,
                            float fy, float cx, float cy, float width, float height, float *us,
-                           float *cinv2ds, float *colors, float *depths, int32_t *areas, gsb_stream_t stream);
+                           float *cinv2ds, float *colors, float *depths, int32_t *areas, const float *alphas,
+                           void *records, gsb_stream_t stream);
 int gsb_preprocess_backward(int N, int sh_dim3, const float *pws, const float *rots, const float *scales,
                             const float *shs, const float *Rcw, const float *tcw, const float *twc, float fx,
                             float fy, float cx, float cy, float width, float height, const float *dloss_dus,
                             const float *dloss_dcinv2ds, const float *dloss_dcolors, float *dloss_dpws,
-                            float *dloss_dshs, float *dloss_dscales, float *dloss_drots, gsb_stream_t stream);
+                            float *dloss_dshs, float *dloss_dscales, float *dloss_drots, const float *moments,
+                            const float *cinv2ds, float *dloss_dus_out, float *dloss_dalphas_out,
+                            gsb_stream_t stream);
 
 /* ---- splat, phase 1: tile rectangles + patch count.
  * Replaces getRects + thrust::inclusive_scan + the D2H read of the total
@@ -116,14 +127,15 @@ int gsb_splat_bin(int H, int W, int N, const float *us, float *depths, int32_t *
  * Every output element is written (no pre-zeroing needed).
  * depth_key_max: the value phase 1 returned (bounds the sort width; keys are packed into 32
  * bits when tile and depth bits fit), or 0xFFFFFFFF for the reference's full 64-bit layout --
- * the resulting order is the same.  After the call the N packed 48-B per-Gaussian records the
- * rasterizers gather from sit at ws + gsb_splat_records_offset(...) and may be handed to
- * gsb_splat_backward as `packed_records` while `ws` and the inputs are unchanged. */
+ * the resulting order is the same.  packed_records: NULL, or the per-Gaussian records
+ * gsb_preprocess_forward wrote.  With NULL they are built here, sit at
+ * ws + gsb_splat_records_offset(...) after the call and may be handed to gsb_splat_backward as
+ * `packed_records` while `ws` and the inputs are unchanged. */
 size_t gsb_splat_workspace_bytes(int N, int H, int W, int64_t P);
 size_t gsb_splat_records_offset(int N, int H, int W, int64_t P);
 int gsb_splat_render(int H, int W, int N, int64_t P, uint32_t depth_key_max, const float *us,
                      const float *cinv2ds, const float *alphas, const float *depths, const float *colors,
-                     const void *bin_ws, void *ws, size_t ws_bytes, float *image,
+                     const void *packed_records, const void *bin_ws, void *ws, size_t ws_bytes, float *image,
                      int32_t *contrib, float *final_tau, int32_t *patch_range_per_tile,
                      int32_t *gsid_per_patch, gsb_stream_t stream);
 
@@ -131,7 +143,10 @@ int gsb_splat_render(int H, int W, int N, int64_t P, uint32_t depth_key_max, con
  * Consumes the forward's contrib / final_tau / patch_range_per_tile / gsid_per_patch.
  * -> dloss_dus[N,1,2], dloss_dcinv2ds[N,1,3], dloss_dalphas[N,1,1], dloss_dcolors[N,1,3]
  * (every element written).  packed_records: NULL (the per-Gaussian records are rebuilt from the
- * four attribute arrays into `ws`) or the forward's record array. */
+ * four attribute arrays into `ws`) or the forward's record array.
+ * moments_out: NULL, or [N,9] -- the raw per-Gaussian moment rows are left there and the
+ * conversion to the four gradient tensors is skipped (they may then be NULL): the caller feeds
+ * the rows to gsb_preprocess_backward, which does the conversion in registers. */
 size_t gsb_splat_backward_workspace_bytes(int N, int H, int W, int64_t P);
 int gsb_splat_backward(int H, int W, int N, int64_t P, const float *us, const float *cinv2ds,
                        const float *alphas, const float *colors, const int32_t *contrib,
@@ -139,7 +154,7 @@ int gsb_splat_backward(int H, int W, int N, int64_t P, const float *us, const fl
                        const int32_t *gsid_per_patch, const float *dloss_dgammas,
                        const void *packed_records, void *ws,
                        size_t ws_bytes, float *dloss_dus, float *dloss_dcinv2ds,
-                       float *dloss_dalphas, float *dloss_dcolors, gsb_stream_t stream);
+                       float *dloss_dalphas, float *dloss_dcolors, float *moments_out, gsb_stream_t stream);
 
 /* ---- batched tiny matmul (extension).  C[b] = A[b] (m x k) . B[b] (k x n), or B shared by all
  * batches when b_shared != 0; dense row-major f32.  This is the product the reference's
@@ -245,6 +260,8 @@ int gsb_params_to_gs(int64_t N, const gsb_gaussians *src, float *gs_rows, gsb_st
  * the handles are exchanged between the processes by the caller (any transport) and opened
  * with gsb_comm_open.  regions_host[world]: HOST array of device pointers, entry r = rank r's
  * region as seen from this process (own pointer for r == rank).  world in {1, 2, 4, 8}.
+ * gsb_preprocess_backward_push takes the upstream gradients either as the four dloss_d* tensors
+ * or, like gsb_preprocess_backward, as moments[N,9] + cinv2ds[N,3] (+ dloss_dus_out[N,2]).
  * The kernels spin on flags in peer memory with a 5 s timeout; gsb_exchange_status returns 1
  * if a wait ever timed out (a peer missing) -- the results are then invalid. */
 #define GSB_COMM_HANDLE_BYTES 64
@@ -259,7 +276,8 @@ int gsb_preprocess_backward_push(int N, int sh_dim3, const float *pws, const flo
                                  const float *shs, const float *Rcw, const float *tcw, const float *twc,
                                  float fx, float fy, float cx, float cy, float width, float height,
                                  const float *dloss_dus, const float *dloss_dcinv2ds, const float *dloss_dcolors,
-                                 const float *dloss_dalphas, int world, int rank, void *const *regions_host,
+                                 const float *dloss_dalphas, const float *moments, const float *cinv2ds,
+                                 float *dloss_dus_out, int world, int rank, void *const *regions_host,
                                  uint32_t epoch, gsb_stream_t stream);
 int gsb_grad_reduce_broadcast(int N, int sh_dim3, int world, int rank, void *const *regions_host, uint32_t epoch,
                               gsb_stream_t stream);

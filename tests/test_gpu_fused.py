@@ -186,3 +186,48 @@ def test_record_cache_and_key_widths():
                                     img.data_ptr(), con.data_ptr(), ft.data_ptr(), rg.data_ptr(), gs.data_ptr(), st),
                lib)
     assert torch.equal(gs, out[4]) and torch.equal(rg, out[3]) and torch.equal(img, out[0])
+
+
+def test_fused_shortcuts_match_separate_passes():
+    """preprocess(alphas=...) writes the same per-Gaussian records the pack pass builds, and
+    preprocessB(moments=...) equals finalize + preprocessB on the four gradient tensors"""
+    from easygaussiansplatting_b200 import ops
+    W, H, N = 300, 200, 30000
+    sc = scene(N, W, H, 48, 33)
+    P = [t(sc[k]) for k in ("pws", "rots", "scales", "shs", "Rcw", "tcw", "twc")]
+    cam = (sc["fx"], sc["fy"], sc["cx"], sc["cy"], W, H)
+    al = t(sc["alphas"])
+    plain = ops.preprocess(*P, *cam)
+    withrec = ops.preprocess(*P, *cam, alphas=al)
+    assert len(plain) == 5 and len(withrec) == 6 and tuple(withrec[5].shape) == (N, 12)
+    for a, b in zip(plain, withrec):
+        assert torch.equal(a, b)
+    us, ci, col, d, ar = plain
+    s1 = ops.splat(H, W, us, ci, al, d.clone(), col, ar.clone())
+    ops.clear_record_cache()
+    s2 = ops.splat(H, W, us, ci, al, d.clone(), col, ar.clone(), records=withrec[5])
+    for a, b in zip(s1, s2):
+        assert torch.equal(a, b)
+    dl = t(upstream_gradient(W, H, 5) * (3.0 * W * H))
+    g4 = ops.splatB(H, W, us, ci, al, d, col, s2[1], s2[2], s2[3], s2[4], dl)
+    m = ops.splatB(H, W, us, ci, al, d, col, s2[1], s2[2], s2[3], s2[4], dl, moments_only=True)
+    assert tuple(m.shape) == (N, 9)
+    a = ops.preprocessB(*P, *cam, g4[0], g4[1], g4[3])
+    b = ops.preprocessB(*P, *cam, None, None, None, moments=m, cinv2ds=ci)
+    assert len(a) == 4 and len(b) == 6
+    for x, y in zip(a, b[:4]):
+        assert float((x - y).abs().max() / x.abs().max()) <= 2e-6
+    assert float((b[4] - g4[0].reshape(N, 2)).abs().max() / g4[0].abs().max()) <= 2e-6
+    assert torch.equal(b[5], g4[2].reshape(N))
+    with pytest.raises(RuntimeError, match="go together"):
+        _lib_call_preprocess_with_records_only(ops, P, cam, N)
+
+
+def _lib_call_preprocess_with_records_only(ops, P, cam, N):
+    from easygaussiansplatting_b200 import _lib
+    lib = _lib.load()
+    o = [torch.empty((N, k), device=DEV) for k in (2, 3, 3)] + [torch.empty(N, device=DEV),
+                                                                torch.empty((N, 2), dtype=torch.int32, device=DEV)]
+    rec = torch.empty((N, 12), device=DEV)
+    _lib.check(lib.gsb_preprocess_forward(N, 16, *[x.data_ptr() for x in P], *[float(c) for c in cam],
+                                          *[x.data_ptr() for x in o], None, rec.data_ptr(), None), lib)
