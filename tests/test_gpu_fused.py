@@ -182,7 +182,7 @@ def test_record_cache_and_key_widths():
     img = torch.empty_like(out[0]); con = torch.empty_like(out[1]); ft = torch.empty_like(out[2])
     rg = torch.empty_like(out[3]); gs = torch.empty_like(out[4])
     _lib.check(lib.gsb_splat_render(H, W, N, P, 0xFFFFFFFF, us.data_ptr(), ci.data_ptr(), al.data_ptr(),
-                                    d2.data_ptr(), col.data_ptr(), bin_ws.data_ptr(), ws.data_ptr(), ws_bytes,
+                                    d2.data_ptr(), col.data_ptr(), None, bin_ws.data_ptr(), ws.data_ptr(), ws_bytes,
                                     img.data_ptr(), con.data_ptr(), ft.data_ptr(), rg.data_ptr(), gs.data_ptr(), st),
                lib)
     assert torch.equal(gs, out[4]) and torch.equal(rg, out[3]) and torch.equal(img, out[0])
