@@ -215,10 +215,11 @@ def test_fused_shortcuts_match_separate_passes():
     a = ops.preprocessB(*P, *cam, g4[0], g4[1], g4[3])
     b = ops.preprocessB(*P, *cam, None, None, None, moments=m, cinv2ds=ci)
     assert len(a) == 4 and len(b) == 6
+    # (two backward launches accumulate their moment rows with float atomics in different orders)
     for x, y in zip(a, b[:4]):
-        assert float((x - y).abs().max() / x.abs().max()) <= 2e-6
-    assert float((b[4] - g4[0].reshape(N, 2)).abs().max() / g4[0].abs().max()) <= 2e-6
-    assert torch.equal(b[5], g4[2].reshape(N))
+        assert float((x - y).abs().max() / x.abs().max()) <= 1e-5
+    assert float((b[4] - g4[0].reshape(N, 2)).abs().max() / g4[0].abs().max()) <= 1e-5
+    assert float((b[5] - g4[2].reshape(N)).abs().max() / g4[2].abs().max()) <= 1e-5
     with pytest.raises(RuntimeError, match="go together"):
         _lib_call_preprocess_with_records_only(ops, P, cam, N)
 
