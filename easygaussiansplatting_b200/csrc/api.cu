@@ -490,12 +490,10 @@ int gsb_preprocess_backward_push(int N, int sh_dim3, const float *pws, const flo
   }
   gp.counter = reinterpret_cast<uint32_t *>(static_cast<char *>(regions_host[rank]) + 128);
   gp.g_alphas = dloss_dalphas;
-  gp.rpr = G.rpr;
   gp.off_rots = G.slot_off[1];
   gp.off_pws = G.slot_off[2];
   gp.off_scales = G.slot_off[3];
   gp.off_alphas = G.slot_off[4];
-  gp.tiles_per_rank = G.tiles_per_rank;
   gp.world = world;
   gp.rank = rank;
   gp.epoch = epoch;

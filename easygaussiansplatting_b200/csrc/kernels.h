@@ -79,9 +79,9 @@ struct GradPush {
   float *slot[kMaxWorld];      // staging slot `rank` on each owner
   uint32_t *flags[kMaxWorld];  // arrive[] array of each rank
   uint32_t *counter;
-  const float *g_alphas;
-  long long rpr, off_rots, off_pws, off_scales, off_alphas;
-  int tiles_per_rank, world, rank;
+  const float *g_alphas;       // dL/dalpha of this view (unused when the moment rows are given)
+  long long off_rots, off_pws, off_scales, off_alphas;  // float offsets of the segments inside a slot
+  int world, rank;
   uint32_t epoch;
 };
 int launch_preprocess_bwd_push(int N, int k3, const float *pws, const float *rots, const float *scales,
