@@ -18,7 +18,7 @@
 // torch's CUDA kernels use the same libdevice routines, which keeps the clone / split values
 // within an ulp of the reference's.
 #include <cub/device/device_scan.cuh>
-#include <cub/iterator/transform_input_iterator.cuh>
+#include <thrust/iterator/transform_iterator.h>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -302,7 +302,7 @@ inline int stream_grid(int64_t total, int block) {
 
 size_t density_workspace_bytes(int64_t N) {
   size_t tmp = 0;
-  cub::TransformInputIterator<Slot3, ClsToSlot, const uint8_t *> it(nullptr, ClsToSlot());
+  thrust::transform_iterator<ClsToSlot, const uint8_t *, Slot3> it(static_cast<const uint8_t *>(nullptr), ClsToSlot());
   cub::DeviceScan::ExclusiveScan(nullptr, tmp, it, (Slot3 *)nullptr, SlotAdd(), Slot3{0, 0, 0}, (int)(N > 0 ? N : 1));
   return 256 + tmp;  // [three int64 totals, padded to 256 B][scan temp]
 }
@@ -335,7 +335,7 @@ int launch_density_plan(int64_t N, const float *alphas_raw, const float *scales_
   size_t tmp = ws_bytes - 256;
   {
     ProfScope ps(K_DENSITY_SCAN, st);
-    cub::TransformInputIterator<Slot3, ClsToSlot, const uint8_t *> it(cls, ClsToSlot());
+    thrust::transform_iterator<ClsToSlot, const uint8_t *, Slot3> it(static_cast<const uint8_t *>(cls), ClsToSlot());
     GSB_CUDA_TRY(cub::DeviceScan::ExclusiveScan(scan_tmp, tmp, it, reinterpret_cast<Slot3 *>(slots), SlotAdd(),
                                                Slot3{0, 0, 0}, (int)N, st));
     k_density_totals<<<1, 32, 0, st>>>(N, cls, reinterpret_cast<const Slot3 *>(slots), totals);

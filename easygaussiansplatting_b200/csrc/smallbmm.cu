@@ -11,7 +11,6 @@
 
 namespace gsb {
 
-constexpr int BMM_MAX_MK = 32;  // m * k elements of A held in registers
 constexpr int BMM_THREADS = 128;
 
 template <int M, int K, int NN>
