@@ -11,11 +11,11 @@
 namespace gsb {
 
 constexpr int BWD2_BATCH = 128;
-// A/B (benchmarks/ab_variants.py, config 2): 10 CTAs/SM with 47 registers and no spills beats
-// 12 CTAs/SM at the 40-register cap (0.671 vs 0.693 ms), and loading a batch's Gaussian ids right
-// before the gather beats carrying them in a register across the batch (0.671 vs 0.678 ms).
+// A/B (benchmarks/ab_variants.py, config 2): CTAs/SM @ registers -> kernel ms:
+// 12 @ 40 (spills) 0.693, 10 @ 47 0.669, 9 @ 55 0.661, 8 @ 61 0.667; and loading a batch's Gaussian
+// ids right before the gather beats carrying them in a register across the batch (0.671 vs 0.678).
 #ifndef BWD2_MINBLOCKS
-#define BWD2_MINBLOCKS 10
+#define BWD2_MINBLOCKS 9
 #endif
 #ifndef BWD2_PREFETCH_IDS
 #define BWD2_PREFETCH_IDS 0
