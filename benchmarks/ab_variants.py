@@ -59,19 +59,36 @@ for i in range(lib.gsb_profile_kernels()):
     lib.gsb_profile_read(i, C.byref(ms), C.byref(cnt))
     if cnt.value:
         kern[lib.gsb_profile_kernel_name(i).decode()] = round(ms.value / 5, 4)
-print("RESULT " + json.dumps({"ms_per_step": round(best, 4), "kernels": kern, "checksum": float(P["pws"].grad.abs().sum())}))
+stats = None
+try:
+    raw = C.CDLL(os.environ.get("GSB_LIB") or _lib.LIB_PATH)
+    buf = (C.c_ulonglong * 8)()
+    raw.gsb_debug_bwd3_stats(buf, 1)
+    step(); torch.cuda.synchronize()
+    raw.gsb_debug_bwd3_stats(buf, 1)
+    stats = list(buf)
+except Exception:
+    pass
+print("RESULT " + json.dumps({"ms_per_step": round(best, 4), "kernels": kern, "stats": stats, "checksum": float(P["pws"].grad.abs().sum())}))
 """
 
 
 def main():
     libs = [("default", "")] + sorted((os.path.basename(p)[len("libgsplat_b200_"):-3], p) for p in
                                       glob.glob(os.path.join(ROOT, "easygaussiansplatting_b200", "libgsplat_b200_*.so")))
+    # GSB_AB_ENVS="name:K=V,K2=V2;name2:K=V": the default build under different environment settings
+    envs = {}
+    for spec in filter(None, os.environ.get("GSB_AB_ENVS", "").split(";")):
+        name, kv = spec.split(":", 1)
+        envs[name] = dict(x.split("=", 1) for x in kv.split(","))
+        libs.append((name, ""))
     only = set(sys.argv[1:])
     out = {}
     for name, path in libs:
         if only and name not in only:
             continue
         env = dict(os.environ)
+        env.update(envs.get(name, {}))
         if path:
             env["GSB_LIB"] = path
         r = subprocess.run([sys.executable, "-c", CHILD % ROOT], env=env, capture_output=True, text=True, timeout=600)

@@ -18,6 +18,8 @@
 //   dL/du = -(A Sx + B Sy, B Sx + C Sy),  dL/dconic = (-Sxx/2, -Sxy, -Syy/2).
 // Records that cannot touch the warp's rectangle are culled by the same ballot test as the
 // forward; records where no pixel is active are skipped before any reduction.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "kernels.h"
 #include "tile_io.cuh"
@@ -75,8 +77,15 @@ int launch_draw_backward(int H, int W, int N, const int32_t *ranges, const Rec *
   if (gx <= 0 || gy <= 0 || N <= 0) return 0;
   GSB_CUDA_TRY(cudaMemsetAsync(moments, 0, sizeof(float) * MOM * (size_t)N, st));
   if (recs != nullptr) {
-    int rc = launch_draw_bwd2_kernel(H, W, ranges, recs, gsid, contrib, final_tau, dloss_dgammas, moments,
-                                     tile_counter, st);
+    // GSB_BWD_VARIANT=2 selects the warp-reduction kernel (raster_bwd2.cu) for A/B runs
+    static const int variant = [] {
+      const char *e = getenv("GSB_BWD_VARIANT");
+      return e != nullptr ? atoi(e) : 3;
+    }();
+    int rc = variant == 2 ? launch_draw_bwd2_kernel(H, W, ranges, recs, gsid, contrib, final_tau, dloss_dgammas,
+                                                    moments, tile_counter, st)
+                          : launch_draw_bwd3_kernel(H, W, ranges, recs, gsid, contrib, final_tau, dloss_dgammas,
+                                                    moments, tile_counter, st);
     if (rc) return rc;
   }
   GSB_CUDA_TRY(cudaGetLastError());

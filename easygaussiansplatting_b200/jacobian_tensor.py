@@ -37,6 +37,10 @@ def _fast_matmul(a, b):
         return None
     if a.dtype != torch.float32 or b.dtype != torch.float32 or a.device != b.device:
         return None
+    # the streaming kernel has no autograd node: whenever the product would be recorded (grad mode
+    # on and an operand requires grad -- double backward, a loss on a Jacobian) torch must do it
+    if torch.is_grad_enabled() and (a.requires_grad or b.requires_grad):
+        return None
     B, m, k = a.shape
     if b.dim() == 3:
         if b.shape[0] != B or b.shape[1] != k:
