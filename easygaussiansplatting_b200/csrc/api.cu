@@ -323,9 +323,10 @@ int gsb_splat_backward(int H, int W, int N, int64_t P, const float *us, const fl
   }
   // P == 0: nothing was drawn; the zeroed moment rows finalise to all-zero gradients
   const int64_t T = (int64_t)((W + GSB_TILE - 1) / GSB_TILE) * ((H + GSB_TILE - 1) / GSB_TILE);
-  if (P >= 48 * T) tile_counter = nullptr;  // dense frame: one CTA per tile
+  int *const work_counter = tile_counter;  // the warp-autonomous kernel always pulls from a counter
+  if (P >= 48 * T) tile_counter = nullptr;  // dense frame: one CTA per tile (variants 2 / 3)
   return launch_draw_backward(H, W, N, patch_range_per_tile, P > 0 ? recs : nullptr, gsid_per_patch, contrib, final_tau,
-                              dloss_dgammas, cinv2ds, moments, tile_counter, dloss_dus, dloss_dcinv2ds,
+                              dloss_dgammas, cinv2ds, moments, tile_counter, work_counter, dloss_dus, dloss_dcinv2ds,
                               dloss_dalphas, dloss_dcolors, moments_out == nullptr, st);
 }
 

@@ -16,12 +16,13 @@ constexpr float LOG2E = 1.4426950408889634f;
 
 // Packed per-patch record, 48 B, written by pack_records (binning.cu) in sorted order so a
 // tile's records are one contiguous 16-B aligned span -> one cp.async.bulk per batch.
-//   q0 = (ux, uy, thr, 0)      mean in pixels; thr = log2(alpha / 0.002) (+margin): a pixel can
-//                              reach alpha' >= 0.002 only where -log2(g) <= thr
+//   q0 = (ux, uy, gsid bits, alpha)   mean in pixels, Gaussian id, opacity -- exactly the four
+//                              words the backward's moment phase needs per record (one 16-byte copy)
+//   q1 = (a, b, c, thr)        log2(g) = a dx^2 + b dx dy + c dy^2  (conic pre-scaled by
+//                              -0.5*log2e, -log2e, -0.5*log2e); thr = log2(alpha / 0.002) (+margin):
+//                              a pixel can reach alpha' >= 0.002 only where -log2(g) <= thr
 //                              (+inf: never cull, -inf: never contributes)
-//   q1 = (a, b, c, alpha)      log2(g) = a dx^2 + b dx dy + c dy^2  (conic pre-scaled by
-//                              -0.5*log2e, -log2e, -0.5*log2e), opacity
-//   q2 = (r, g, b, gsid bits)
+//   q2 = (r, g, b, 0)
 struct __align__(16) Rec {
   float4 q0, q1, q2;
 };
@@ -41,13 +42,13 @@ __device__ __forceinline__ float ex2_approx(float x) {
 // alpha' of one record at one pixel -- THE single definition used by forward and backward
 // so both take identical skip decisions (kernel.cu:243-246 / :909-913).
 // Returns g = exp(-maha/2) through *g.
-__device__ __forceinline__ float alpha_prime(const float4 &q1, float dx, float dy, float *g) {
+__device__ __forceinline__ float alpha_prime(const float4 &q1, float alpha, float dx, float dy, float *g) {
   float t = fmaf(q1.y, dy, q1.x * dx);
   float p = fmaf(t, dx, (q1.z * dy) * dy);
   p = fminf(p, 0.0f);  // max(0, maha)
   float gg = ex2_approx(p);
   *g = gg;
-  return fminf(ALPHA_CLAMP, q1.w * gg);
+  return fminf(ALPHA_CLAMP, alpha * gg);
 }
 
 // Can this record reach alpha' >= 0.002 anywhere in the pixel rectangle [bx0,bx1] x [by0,by1]?
@@ -76,7 +77,7 @@ __device__ __forceinline__ bool rec_can_touch(const float4 &q0, const float4 &q1
   if (inside) qmin = 0.f;
   const float X = fmaxf(fabsf(dxl), fabsf(dxh)), Y = fmaxf(fabsf(dyl), fabsf(dyh));
   const float S = fmaf(A * X, X, fmaf(fabsf(B) * X, Y, C * Y * Y));
-  return !(qmin > q0.z + fmaf(2.0e-6f, S, 1.0e-5f));  // NaN anywhere keeps the record
+  return !(qmin > q1.w + fmaf(2.0e-6f, S, 1.0e-5f));  // NaN anywhere keeps the record
 }
 
 // The 48-byte record the rasterizers work from (one per Gaussian).
@@ -97,9 +98,9 @@ __device__ __forceinline__ Rec build_record(float ux, float uy, float A, float B
     }
   }
   Rec r;
-  r.q0 = make_float4(ux, uy, thr, 0.f);
-  r.q1 = make_float4(-0.5f * LOG2E * A, -LOG2E * B, -0.5f * LOG2E * C, al);
-  r.q2 = make_float4(cr, cg, cb, __int_as_float(id));
+  r.q0 = make_float4(ux, uy, __int_as_float(id), al);
+  r.q1 = make_float4(-0.5f * LOG2E * A, -LOG2E * B, -0.5f * LOG2E * C, thr);
+  r.q2 = make_float4(cr, cg, cb, 0.f);
   return r;
 }
 

@@ -143,15 +143,16 @@ int launch_pack_only(int64_t P, const int32_t *gsid_per_patch, const float *us, 
 int launch_draw_bwd2_kernel(int H, int W, const int32_t *ranges, const Rec *recs, const int32_t *gsid,
                             const int32_t *contrib, const float *final_tau, const float *dloss_dgammas,
                             float *moments, int *tile_counter, cudaStream_t st);
-int launch_draw_bwd3_kernel(int H, int W, const int32_t *ranges, const Rec *recs, const int32_t *gsid,
+int launch_draw_bwd4_kernel(int H, int W, const int32_t *ranges, const Rec *recs, const int32_t *gsid,
                             const int32_t *contrib, const float *final_tau, const float *dloss_dgammas,
-                            float *moments, int *tile_counter, cudaStream_t st);
+                            float *moments, int *work_counter, cudaStream_t st);
 int launch_draw(int H, int W, const int32_t *ranges, const Rec *recs, const int32_t *gsid, float *image,
                 int32_t *contrib, float *final_tau, int *tile_counter, cudaStream_t st);
 int launch_draw_backward(int H, int W, int N, const int32_t *ranges, const Rec *recs, const int32_t *gsid,
                          const int32_t *contrib,
                          const float *final_tau, const float *dloss_dgammas, const float *cinv2ds,
-                         float *moments, int *tile_counter, float *dloss_dus, float *dloss_dcinv2ds,
-                         float *dloss_dalphas, float *dloss_dcolors, bool finalize, cudaStream_t st);
+                         float *moments, int *tile_counter, int *work_counter, float *dloss_dus,
+                         float *dloss_dcinv2ds, float *dloss_dalphas, float *dloss_dcolors, bool finalize,
+                         cudaStream_t st);
 
 }  // namespace gsb

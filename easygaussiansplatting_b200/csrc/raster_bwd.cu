@@ -71,21 +71,22 @@ __global__ void __launch_bounds__(PG) k_finalize_grads(int N, const float *__res
 int launch_draw_backward(int H, int W, int N, const int32_t *ranges, const Rec *recs, const int32_t *gsid,
                          const int32_t *contrib,
                          const float *final_tau, const float *dloss_dgammas, const float *cinv2ds,
-                         float *moments, int *tile_counter, float *dloss_dus, float *dloss_dcinv2ds,
-                         float *dloss_dalphas, float *dloss_dcolors, bool finalize, cudaStream_t st) {
+                         float *moments, int *tile_counter, int *work_counter, float *dloss_dus,
+                         float *dloss_dcinv2ds, float *dloss_dalphas, float *dloss_dcolors, bool finalize,
+                         cudaStream_t st) {
   const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
   if (gx <= 0 || gy <= 0 || N <= 0) return 0;
   GSB_CUDA_TRY(cudaMemsetAsync(moments, 0, sizeof(float) * MOM * (size_t)N, st));
   if (recs != nullptr) {
-    // GSB_BWD_VARIANT=2 selects the warp-reduction kernel (raster_bwd2.cu) for A/B runs
+    // GSB_BWD_VARIANT=2 selects the older warp-reduction kernel (raster_bwd2.cu) for A/B runs
     static const int variant = [] {
       const char *e = getenv("GSB_BWD_VARIANT");
-      return e != nullptr ? atoi(e) : 3;
+      return e != nullptr ? atoi(e) : 4;
     }();
-    int rc = variant == 2 ? launch_draw_bwd2_kernel(H, W, ranges, recs, gsid, contrib, final_tau, dloss_dgammas,
-                                                    moments, tile_counter, st)
-                          : launch_draw_bwd3_kernel(H, W, ranges, recs, gsid, contrib, final_tau, dloss_dgammas,
-                                                    moments, tile_counter, st);
+    int rc = variant == 2   ? launch_draw_bwd2_kernel(H, W, ranges, recs, gsid, contrib, final_tau, dloss_dgammas,
+                                                      moments, tile_counter, st)
+                            : launch_draw_bwd4_kernel(H, W, ranges, recs, gsid, contrib, final_tau, dloss_dgammas,
+                                                      moments, work_counter, st);
     if (rc) return rc;
   }
   GSB_CUDA_TRY(cudaGetLastError());

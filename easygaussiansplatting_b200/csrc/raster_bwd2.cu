@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(128, BWD2_MINBLOCKS) k_draw_bwd2(
             const float2 t = __ffma2_rn(g2s(q1.y), g2s(dy), __fmul2_rn(g2s(q1.x), dx));
             const float2 p = __ffma2_rn(t, dx, g2s(cdy2));
             const float2 gg = g2(ex2_approx(fminf(p.x, 0.0f)), ex2_approx(fminf(p.y, 0.0f)));
-            const float2 ag = __fmul2_rn(g2s(q1.w), gg);
+            const float2 ag = __fmul2_rn(g2s(q0.w), gg);
             const float ap0 = fminf(ALPHA_CLAMP, ag.x), ap1 = fminf(ALPHA_CLAMP, ag.y);
             const bool a0 = (idx < cont0) && (ap0 >= ALPHA_SKIP);
             const bool a1 = (idx < cont1) && (ap1 >= ALPHA_SKIP);
@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(128, BWD2_MINBLOCKS) k_draw_bwd2(
             const float v[9] = {wdx.x + wdx.y, wdy.x + wdy.y, m2.x + m2.y, m3.x + m3.y, m4.x + m4.y,
                                 m5.x + m5.y, m6.x + m6.y, m7.x + m7.y, m8.x + m8.y};
             const float tot = split_reduce9_v2(v, lane);
-            if (slot >= 0) atomicAdd(mom_lane + (size_t)__float_as_int(q2.w) * MOM2, tot);
+            if (slot >= 0) atomicAdd(mom_lane + (size_t)__float_as_int(q0.z) * MOM2, tot);
           }
         }
       }

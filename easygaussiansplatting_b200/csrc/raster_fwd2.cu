@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(128) k_draw2(int W, int H, int gx, int T, cons
               const float2 t = __ffma2_rn(f2s(q1.y), f2s(dy), __fmul2_rn(f2s(q1.x), dx));
               const float2 p = __ffma2_rn(t, dx, f2s(cdy2));
               const float g0 = ex2_approx(fminf(p.x, 0.0f)), g1 = ex2_approx(fminf(p.y, 0.0f));
-              const float2 ag = __fmul2_rn(f2s(q1.w), f2(g0, g1));
+              const float2 ag = __fmul2_rn(f2s(q0.w), f2(g0, g1));
               const float ap0 = fminf(ALPHA_CLAMP, ag.x), ap1 = fminf(ALPHA_CLAMP, ag.y);
               const bool c0p = (tau.x >= TAU_STOP) && (ap0 >= ALPHA_SKIP);
               const bool c1p = (tau.y >= TAU_STOP) && (ap1 >= ALPHA_SKIP);
