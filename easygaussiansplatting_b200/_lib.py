@@ -37,6 +37,8 @@ SIGNATURES = {
     "gsb_splat_render": (_i, [_i, _i, _i, _i64, C.c_uint32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _vp,
                               _vp, _vp, _vp, _vp]),
     "gsb_splat_backward_workspace_bytes": (_sz, [_i, _i, _i, _i64]),
+    "gsb_splat_forward": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, C.c_uint32, _vp, _sz, _vp, _sz,
+                               _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gsb_splat_backward": (_i, [_i, _i, _i, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                 _sz, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gsb_small_bmm": (_i, [C.c_longlong, _i, _i, _i, _vp, _vp, _i, _vp, _vp]),

@@ -31,7 +31,7 @@ struct EvPair { cudaEvent_t a, b; };
 static std::vector<EvPair> g_events[K_COUNT];
 static std::mutex g_prof_mu;
 static const char *const g_names[K_COUNT] = {"project", "computeCov3D", "computeCov2D", "sh2Color",
-                                             "inverseCov2D", "rects", "scan(cub)", "keys", "sort(cub)",
+                                             "inverseCov2D", "rects+scan", "scan(unused)", "keys", "sort",
                                              "ranges", "pack_records", "draw", "draw_backward",
                                              "preprocess_forward", "preprocess_backward",
                                              "finalize_splat_grads", "gau_loss_forward", "gau_loss_backward",
@@ -225,10 +225,11 @@ int gsb_splat_bin(int H, int W, int N, const float *us, float *depths, int32_t *
   cudaStream_t st = (cudaStream_t)stream;
   int rc = launch_bin(H, W, N, us, depths, areas, bin_ws, L, st);
   if (rc) return rc;
-  uint32_t total[2] = {0, 0};  // [patch count, largest depth key]
-  GSB_CUDA_TRY(cudaMemcpyAsync(total, static_cast<char *>(bin_ws) + L.total, 2 * sizeof(uint32_t),
+  uint32_t total[3] = {0, 0, 0};  // [patch count, largest depth key, flags]
+  GSB_CUDA_TRY(cudaMemcpyAsync(total, static_cast<char *>(bin_ws) + L.total, 3 * sizeof(uint32_t),
                                cudaMemcpyDeviceToHost, st));
   GSB_CUDA_TRY(cudaStreamSynchronize(st));
+  GSB_REQUIRE((total[2] & 1u) == 0 && total[0] < (1u << 30), "splat: more than 2^30 patches");
   *P_host = (int64_t)total[0];
   if (depth_key_max_host) *depth_key_max_host = total[1];
   return 0;
@@ -265,7 +266,7 @@ int gsb_splat_render(int H, int W, int N, int64_t P, uint32_t depth_key_max, con
   const BinLayout BL = bin_layout(N);
   GSB_REQUIRE((reinterpret_cast<uintptr_t>(packed_records) & 15) == 0, "splat: packed_records misaligned");
   int rc = launch_sort_and_pack(H, W, N, P, depth_key_max, us, cinv2ds, alphas, depths, colors, bin_ws, BL, ws, SL,
-                                patch_range_per_tile, gsid_per_patch, packed_records == nullptr, st);
+                                patch_range_per_tile, gsid_per_patch, packed_records == nullptr, nullptr, st);
   if (rc) return rc;
   const Rec *recs = P > 0 ? reinterpret_cast<const Rec *>(static_cast<char *>(ws) + SL.recs) : nullptr;
   if (P > 0 && packed_records != nullptr) recs = static_cast<const Rec *>(packed_records);
@@ -279,6 +280,58 @@ int gsb_splat_render(int H, int W, int N, int64_t P, uint32_t depth_key_max, con
   const int64_t T = (int64_t)((W + GSB_TILE - 1) / GSB_TILE) * ((H + GSB_TILE - 1) / GSB_TILE);
   if (P >= 48 * T) tile_counter = nullptr;
   return launch_draw(H, W, patch_range_per_tile, recs, gsid_per_patch, image, contrib, final_tau, tile_counter, st);
+}
+
+int gsb_splat_forward(int H, int W, int N, const float *us, const float *cinv2ds, const float *alphas,
+                      float *depths, const float *colors, int32_t *areas, const void *packed_records,
+                      int64_t P_cap, uint32_t depth_key_cap, void *bin_ws, size_t bin_ws_bytes, void *ws,
+                      size_t ws_bytes, float *image, int32_t *contrib, float *final_tau,
+                      int32_t *patch_range_per_tile, int32_t *gsid_per_patch, uint32_t *status_host,
+                      gsb_stream_t stream) {
+  GSB_REQUIRE(N >= 0 && H > 0 && W > 0 && P_cap > 0 && P_cap < ((int64_t)1 << 30), "splat_forward: bad N/H/W/P_cap");
+  GSB_REQUIRE(image && contrib && final_tau && patch_range_per_tile && gsid_per_patch && status_host && bin_ws && ws,
+              "splat_forward: null pointer");
+  GSB_REQUIRE(N == 0 || (us && cinv2ds && alphas && depths && colors && areas), "splat_forward: null pointer");
+  GSB_REQUIRE((reinterpret_cast<uintptr_t>(packed_records) & 15) == 0, "splat_forward: packed_records misaligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  const BinLayout BL = bin_layout(N);
+  GSB_REQUIRE(bin_ws_bytes >= BL.bytes, "splat_forward: bin workspace too small");
+  SortLayout SL{};
+  int rc = sort_layout(N, H, W, P_cap, &SL);
+  if (rc) return rc;
+  GSB_REQUIRE(ws_bytes >= SL.bytes, "splat_forward: workspace too small");
+  static thread_local cudaEvent_t ready = nullptr;
+  if (ready == nullptr) GSB_CUDA_TRY(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+  const StatusRead sr{status_host, ready};
+  status_host[0] = status_host[1] = status_host[2] = 0;
+  rc = launch_bin(H, W, N, us, depths, areas, bin_ws, BL, st);
+  if (rc) return rc;
+  if (N == 0) {  // nothing to bin: every tile is empty
+    GSB_CUDA_TRY(cudaMemsetAsync(patch_range_per_tile, 0,
+                                 sizeof(int32_t) * 2 * (size_t)((W + GSB_TILE - 1) / GSB_TILE) * ((H + GSB_TILE - 1) / GSB_TILE), st));
+    return launch_draw(H, W, patch_range_per_tile, nullptr, gsid_per_patch, image, contrib, final_tau,
+                       static_cast<int *>(ws), st);
+  }
+  rc = launch_sort_and_pack(H, W, N, P_cap, depth_key_cap, us, cinv2ds, alphas, depths, colors, bin_ws, BL, ws, SL,
+                            patch_range_per_tile, gsid_per_patch, packed_records == nullptr, &sr, st);
+  if (rc) return rc;
+  const Rec *recs = packed_records != nullptr ? static_cast<const Rec *>(packed_records)
+                                              : reinterpret_cast<const Rec *>(static_cast<char *>(ws) + SL.recs);
+  // sparse frame -> persistent tile queue; the host does not know P yet, the capacity stands in
+  int *tile_counter = reinterpret_cast<int *>(static_cast<char *>(ws) + SL.counters);
+  const int64_t T = (int64_t)((W + GSB_TILE - 1) / GSB_TILE) * ((H + GSB_TILE - 1) / GSB_TILE);
+  if (P_cap >= 60 * T) tile_counter = nullptr;
+  rc = launch_draw(H, W, patch_range_per_tile, recs, gsid_per_patch, image, contrib, final_tau, tile_counter, st);
+  if (rc) return rc;
+  // the sort and the rasterizer are queued; now look at what the binning found
+  GSB_CUDA_TRY(cudaEventSynchronize(ready));
+  if ((status_host[2] & 1u) != 0 || status_host[0] >= (1u << 30)) return set_arg_error("splat: more than 2^30 patches");
+  if ((status_host[2] & 6u) != 0 || (int64_t)status_host[0] > P_cap) {
+    snprintf(g_err, sizeof(g_err), "splat_forward: capacity exceeded (P = %u of %lld, flags %u)", status_host[0],
+             (long long)P_cap, status_host[2]);
+    return GSB_CAPACITY_EXCEEDED;
+  }
+  return 0;
 }
 
 size_t gsb_splat_backward_workspace_bytes(int N, int H, int W, int64_t P) {

@@ -121,20 +121,29 @@ int launch_params_to_gs(int64_t N, float *const *src, float *gs, cudaStream_t st
 
 // ---- binning (binning.cu)
 struct BinLayout {  // carve-up of the phase-1 workspace
-  size_t rects, counts, offsets, total, scan_tmp, scan_tmp_bytes, bytes;
+  size_t rects, offsets, total, scan_desc, bytes;  // total: [P, max depth key, flags, scan claim] u32
 };
 BinLayout bin_layout(int N);
 int launch_bin(int H, int W, int N, const float *us, float *depths, int32_t *areas, void *ws,
                const BinLayout &L, cudaStream_t st);
 
 struct SortLayout {  // carve-up of the phase-2 workspace
-  size_t keys_a, keys_b, vals_a, recs, counters, sort_tmp, sort_tmp_bytes, bytes;
+  size_t keys_a, keys_b, vals_a, vals_b, recs, counters;
+  size_t sort_state, sort_state_bytes, hist, desc, desc_stride;  // radix-sort state, zeroed per call
+  size_t bytes;
 };
 int sort_layout(int N, int H, int W, int64_t P, SortLayout *out);
+// capacity-based path: where to copy [P, max depth key, flags] for the host, and the event that
+// tells it the copy has landed (recorded right after the key kernel)
+struct StatusRead {
+  uint32_t *host;
+  cudaEvent_t ready;
+};
 int launch_sort_and_pack(int H, int W, int N, int64_t P, uint32_t depth_key_max, const float *us,
                          const float *cinv2ds, const float *alphas, const float *depths, const float *colors,
                          const void *bin_ws, const BinLayout &BL, void *ws, const SortLayout &SL,
-                         int32_t *ranges, int32_t *gsid_per_patch, bool pack, cudaStream_t st);
+                         int32_t *ranges, int32_t *gsid_per_patch, bool pack, const StatusRead *sr,
+                         cudaStream_t st);
 int launch_pack_only(int64_t P, const int32_t *gsid_per_patch, const float *us, const float *cinv2ds,
                      const float *alphas, const float *colors, Rec *recs, cudaStream_t st);
 

@@ -104,7 +104,7 @@ class GSFunctionFused(torch.autograd.Function):
             pws, rots, scales, shs, cam.Rcw, cam.tcw, cam.twc, cam.fx, cam.fy, cam.cx, cam.cy,
             cam.width, cam.height, alphas=alphas)
         image, contrib, final_tau, patch_range_per_tile, gsid_per_patch = ops.splat(
-            cam.height, cam.width, us, cinv2ds, alphas, depths, colors, areas, records=records)
+            cam.height, cam.width, us, cinv2ds, alphas, depths, colors, areas, records=records, capacity=True)
         ctx.cam = cam
         ctx.alpha_shape = alphas.shape
         ctx.save_for_backward(pws, shs, alphas, scales, rots, us, cinv2ds, depths, colors, contrib,

@@ -155,12 +155,27 @@ def inverseCov2D(cov2ds, depths, calc_J):
     return [cinv, areas, _jac(J)] if calc_J else [cinv, areas]
 
 
-def splat(height, width, us, cinv2ds, alphas, depths, colors, areas, records=None):
+GSB_CAPACITY_EXCEEDED = 2
+_CAPACITY = {}  # (device index, H, W, N) -> (P_cap, depth_key_cap) learnt from the previous frame
+_STATUS = {}    # device index -> pinned int32[4] for gsb_splat_forward's status read
+
+
+def _next_capacity(P, dkmax):
+    """Bounds for the next frame of the same shape: 25 % head-room on the patch count, and the key
+    width the exact path would pick for this frame's largest depth key."""
+    bits = max(int(dkmax), 1).bit_length()
+    return int(P * 1.25) + 4096, (1 << bits) - 1
+
+
+def splat(height, width, us, cinv2ds, alphas, depths, colors, areas, records=None, capacity=False):
     """ext.cpp:10-18.  MUTATES depths / areas for Gaussians that touch no tile
     (kernel.cu:114-119).  -> [image[3,H,W], contrib[H,W] i32, final_tau[H,W],
     patch_range_per_tile[T,2] i32, gsid_per_patch[P] i32]
     records (extension): the packed per-Gaussian records `preprocess(..., alphas=...)` wrote;
-    the pack pass is then skipped."""
+    the pack pass is then skipped.
+    capacity (extension): size the sort from the previous frame of the same shape
+    (gsb_splat_forward) instead of reading the patch count back in the middle of the frame; a
+    frame that outgrows the bound is transparently redone the exact way."""
     H, W = int(height), int(width)
     if H <= 0 or W <= 0:
         raise ValueError("height and width must be positive")
@@ -176,6 +191,45 @@ def splat(height, width, us, cinv2ds, alphas, depths, colors, areas, records=Non
     dev = us.device
     T = ((W + 15) // 16) * ((H + 15) // 16)
     lib = _L()
+    if records is not None:
+        records = _chk(records, "records", last=12, ndim=2)
+        if records.shape[0] != N:
+            raise ValueError("records must be [N, 12]")
+    cap_key = (dev.index, H, W, N)
+    if capacity and cap_key in _CAPACITY and N > 0:
+        P_cap, dk_cap = _CAPACITY[cap_key]
+        with torch.cuda.device(dev):
+            st = _stream()
+            status = _STATUS.get(dev.index)
+            if status is None:
+                status = _STATUS[dev.index] = torch.zeros(4, dtype=torch.int32).pin_memory()
+            bin_bytes = lib.gsb_splat_bin_workspace_bytes(N)
+            bin_ws = torch.empty((bin_bytes,), dtype=torch.uint8, device=dev)
+            ws_bytes = lib.gsb_splat_workspace_bytes(N, H, W, P_cap)
+            ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+            image = torch.empty((3, H, W), dtype=torch.float32, device=dev)
+            contrib = torch.empty((H, W), dtype=torch.int32, device=dev)
+            final_tau = torch.empty((H, W), dtype=torch.float32, device=dev)
+            ranges = torch.empty((T, 2), dtype=torch.int32, device=dev)
+            gsid = torch.empty((P_cap,), dtype=torch.int32, device=dev)
+            rc = lib.gsb_splat_forward(H, W, N, _ptr(us), _ptr(cinv2ds), _ptr(alphas), _ptr(depths), _ptr(colors),
+                                       _ptr(areas), _ptr(records), P_cap, dk_cap, _ptr(bin_ws), bin_bytes, _ptr(ws),
+                                       ws_bytes, _ptr(image), _ptr(contrib), _ptr(final_tau), _ptr(ranges),
+                                       _ptr(gsid), status.data_ptr(), st)
+            if rc == 0:
+                P, dkmax = int(status[0]) & 0xffffffff, int(status[1]) & 0xffffffff
+                _CAPACITY[cap_key] = _next_capacity(P, dkmax)
+                gsid = gsid[:P]
+                if P > 0:
+                    if records is not None:
+                        _remember_records(gsid, records, 0, (us, cinv2ds, alphas, colors))
+                    else:
+                        _remember_records(gsid, ws, lib.gsb_splat_records_offset(N, H, W, P_cap),
+                                          (us, cinv2ds, alphas, colors))
+                return [image, contrib, final_tau, ranges, gsid]
+            if rc != GSB_CAPACITY_EXCEEDED:
+                _lib.check(rc, lib)
+            del _CAPACITY[cap_key]  # outgrown: this frame the exact way (the in-place culls are idempotent)
     with torch.cuda.device(dev):
         st = _stream()
         bin_bytes = lib.gsb_splat_bin_workspace_bytes(N)
@@ -191,10 +245,8 @@ def splat(height, width, us, cinv2ds, alphas, depths, colors, areas, records=Non
         final_tau = torch.empty((H, W), dtype=torch.float32, device=dev)
         ranges = torch.empty((T, 2), dtype=torch.int32, device=dev)
         gsid = torch.empty((P,), dtype=torch.int32, device=dev)
-        if records is not None:
-            records = _chk(records, "records", last=12, ndim=2)
-            if records.shape[0] != N:
-                raise ValueError("records must be [N, 12]")
+        if capacity:
+            _CAPACITY[cap_key] = _next_capacity(P, dkmax.value)
         _lib.check(lib.gsb_splat_render(H, W, N, P, dkmax.value, _ptr(us), _ptr(cinv2ds), _ptr(alphas),
                                         _ptr(depths), _ptr(colors), _ptr(records), _ptr(bin_ws), _ptr(ws), ws_bytes,
                                         _ptr(image), _ptr(contrib), _ptr(final_tau), _ptr(ranges), _ptr(gsid),

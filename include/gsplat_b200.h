@@ -139,6 +139,27 @@ int gsb_splat_render(int H, int W, int N, int64_t P, uint32_t depth_key_max, con
                      int32_t *contrib, float *final_tau, int32_t *patch_range_per_tile,
                      int32_t *gsid_per_patch, gsb_stream_t stream);
 
+/* ---- splat, both phases without the mid-way host round trip (extension).
+ * gsb_splat_bin + gsb_splat_render stall the GPU while the host reads P back to size the sort
+ * workspace (the reference does the same, gausplat.cu:64-67).  Here the caller provides CAPACITIES
+ * instead -- an upper bound P_cap on the patch count (e.g. 1.25 x the previous frame's P) and on the
+ * depth keys (depth_key_cap >= every (uint32)(depth*1000); it fixes the key width) -- all kernels
+ * read the actual P from device memory, and the host looks at [P, max depth key, flags] only
+ * after the sort and the rasterizer have been enqueued behind the copy: no GPU bubble.
+ * Workspaces: bin_ws as for gsb_splat_bin; ws >= gsb_splat_workspace_bytes(N, H, W, P_cap);
+ * gsid_per_patch[P_cap] (the first P entries are valid).  status_host[3] (pinned memory for a truly
+ * asynchronous copy) receives P, the largest depth key and the flags.
+ * Returns 0, or GSB_CAPACITY_EXCEEDED when a bound was too small: the outputs are then undefined and
+ * the caller repeats the frame with gsb_splat_bin / gsb_splat_render (or larger capacities);
+ * depths / areas have been culled in place exactly as gsb_splat_bin does, which is idempotent. */
+#define GSB_CAPACITY_EXCEEDED 2
+int gsb_splat_forward(int H, int W, int N, const float *us, const float *cinv2ds, const float *alphas,
+                      float *depths, const float *colors, int32_t *areas, const void *packed_records,
+                      int64_t P_cap, uint32_t depth_key_cap, void *bin_ws, size_t bin_ws_bytes, void *ws,
+                      size_t ws_bytes, float *image, int32_t *contrib, float *final_tau,
+                      int32_t *patch_range_per_tile, int32_t *gsid_per_patch, uint32_t *status_host,
+                      gsb_stream_t stream);
+
 /* ---- splatB.  Replaces `splatB` (ext.cpp:20-32, gausplat.cu:114-159, kernel.cu:809-950).
  * Consumes the forward's contrib / final_tau / patch_range_per_tile / gsid_per_patch.
  * -> dloss_dus[N,1,2], dloss_dcinv2ds[N,1,3], dloss_dalphas[N,1,1], dloss_dcolors[N,1,3]

@@ -39,6 +39,11 @@ def num_threads():
     return int(lib().orc_num_threads())
 
 
+def set_num_threads(n):
+    """OpenMP threads of every later call (bench.py: os.cpu_count(), whatever OMP_NUM_THREADS says)."""
+    lib().orc_set_num_threads(int(n))
+
+
 def _f32(a):
     return np.ascontiguousarray(a, dtype=np.float32)
 

@@ -232,3 +232,38 @@ def _lib_call_preprocess_with_records_only(ops, P, cam, N):
     rec = torch.empty((N, 12), device=DEV)
     _lib.check(lib.gsb_preprocess_forward(N, 16, *[x.data_ptr() for x in P], *[float(c) for c in cam],
                                           *[x.data_ptr() for x in o], None, rec.data_ptr(), None), lib)
+
+
+@pytest.mark.parametrize("N,W,H", [(20000, 320, 240), (400, 1000, 700)])
+def test_capacity_path_equals_exact_path(N, W, H):
+    """gsb_splat_forward (sort sized from the previous frame, status read after everything is
+    enqueued) gives bit-identical outputs to gsb_splat_bin + gsb_splat_render; a frame that outgrows
+    its bounds -- patch count or depth-key width -- is redone the exact way."""
+    from easygaussiansplatting_b200 import ops
+    sc = scene(N, W, H, 12, 5)
+    args = (t(sc["pws"]), t(sc["rots"]), t(sc["scales"]), t(sc["shs"]), t(sc["Rcw"]), t(sc["tcw"]), t(sc["twc"]),
+            sc["fx"], sc["fy"], sc["cx"], sc["cy"], W, H)
+    al = t(sc["alphas"])
+
+    def run(capacity):
+        u, ci, col, dep, ar = ops.preprocess(*args)
+        return ops.splat(H, W, u, ci, al, dep, col, ar, capacity=capacity), dep, ar
+
+    ops._CAPACITY.clear()
+    exact, dep0, ar0 = run(False)
+    first, _, _ = run(True)   # learns the capacities (exact path)
+    key = (0, H, W, N)
+    assert key in ops._CAPACITY
+    cap, dep1, ar1 = run(True)  # capacity path
+    assert ops._CAPACITY[key][0] >= cap[4].numel()
+    for a, b, c in zip(exact, first, cap):
+        assert torch.equal(a, b) and torch.equal(a, c)
+    assert torch.equal(dep0, dep1) and torch.equal(ar0, ar1)
+    P = exact[4].numel()
+    ops._CAPACITY[key] = (max(1, P // 3), ops._CAPACITY[key][1])  # too few patches
+    small, _, _ = run(True)
+    ops._CAPACITY[key] = (2 * P + 10, 3)                          # depth keys wider than planned
+    narrow, _, _ = run(True)
+    for a, b, c in zip(exact, small, narrow):
+        assert torch.equal(a, b) and torch.equal(a, c)
+    assert ops._CAPACITY[key][0] >= P  # relearnt
