@@ -4,9 +4,11 @@
 #   baseline/_ref/gsplatcu*.so   the reference's CUDA extension (gsplatcu/setup.py:4-14) built
 #                                for sm_100a -- benchmarks/compare_ref_gpu.py times it next to
 #                                ours on the same B200 ("B-REF-GPU" in BASELINE.md)
-#   baseline/_ref/py/            the reference's pure-Python package gsplat/ and train.py, so
-#                                benchmarks/train_reference.py can run the reference's own
-#                                training script (BASELINE config 3) on either gsplatcu
+#   baseline/_ref/py/            the reference's pure-Python package gsplat/, train.py and its
+#                                forward_gpu.py / backward_gpu.py / backward_cpu.py / forward_cpu.py, so
+#                                benchmarks/train_reference.py and run_reference_scripts.py can run the
+#                                reference's own scripts (BASELINE config 3, the 19-line [OK] parity
+#                                script) on either gsplatcu
 # The reference tree is read-only, so the build runs from a scratch copy under /tmp.  No
 # reference source enters this repository's history.  Only runs where /root/reference exists
 # (the dev container).   usage: build_ref_gpu.sh [py]   ("py": only refresh baseline/_ref/py)
@@ -18,6 +20,8 @@ mkdir -p "$OUT/py"
 rm -rf "$OUT/py/gsplat"
 cp -r "$REF/gsplat" "$OUT/py/gsplat"
 cp "$REF/train.py" "$OUT/py/train.py"
+# the reference's own parity / inference scripts (benchmarks/run_reference_scripts.py runs them unmodified)
+for f in forward_gpu.py backward_gpu.py backward_cpu.py forward_cpu.py; do cp "$REF/$f" "$OUT/py/$f"; done
 find "$OUT/py" -name __pycache__ -prune -exec rm -rf {} +
 if [ "${1:-}" = "py" ]; then ls "$OUT" "$OUT/py"; exit 0; fi
 TMP=$(mktemp -d /tmp/refgsplatcu.XXXXXX)

@@ -13,10 +13,16 @@ ours, N == 1   config[1] of BASELINE.json: 1M synthetic Gaussians, 1920x1080, SH
                (GSFunction mirror of gsplat/gsmodel.py:6-93) is reported beside it as
                `op_surface` (that is what the unmodified reference scripts exercise).
 ours, N  > 1   multi-view data parallel: the same shared Gaussians, one camera per
-               rank per step, NCCL all-reduce (sum) of the parameter gradients; weak scaling
-               in views, value = total pixels of all ranks / max-over-ranks time.
-reference      the CPU restatement of the reference algorithm (oracle/, OpenMP, all host
-               threads) on a bounded crop of the same workload; rank 0 only.
+               rank per step, the parameter gradients summed over the ranks by the factorised
+               exchange (parallel.MultiViewStep: all-reduce of 44 B/Gaussian + all-gather of the
+               12 B/Gaussian dL/dcolor of every view, dL/dsh re-expanded locally); weak scaling
+               in views, value = total pixels of all ranks / max-over-ranks time.  The flat
+               236 B/Gaussian NCCL all-reduce and the peer-memory exchange are timed beside it.
+               `config5`: BASELINE config 5 as written (2M shared Gaussians, 8 cameras per step
+               split over the ranks, ONE exchange per step) at every N.
+reference      the CPU restatement of the reference algorithm (oracle/, OpenMP pinned to every
+               host core) on the SAME workload (whole 1920x1080 frame, all 1M Gaussians,
+               forward + backward); rank 0 only.
 Prints ONE JSON line (rank 0).
 """
 import argparse
@@ -36,8 +42,9 @@ sys.path.insert(0, ROOT)
 
 METRIC = "rendered Mpixels/s fwd+bwd @1M Gaussians 1080p; grad max-rel-err vs CPU"
 N_GAUSS, WIDTH, HEIGHT, SH_DIM = 1_000_000, 1920, 1080, 48
-CROP_ROWS = 128  # CPU sample: rows [476, 604) of the frame (8 tile rows, 11.9 % of the pixels)
-CROP_Y0 = 476
+CROP_ROWS = HEIGHT  # CPU arm: the whole frame (a few seconds per pass with OpenMP on the host cores)
+CROP_Y0 = 0
+CPU_BUDGET_S = 150.0  # the reference arm stops adding timed passes once this much CPU time is spent
 
 
 def peaks():
@@ -50,18 +57,22 @@ def peaks():
 # ------------------------------------------------------------------ CPU arm (oracle port)
 def cpu_sample(steps=1, warmup=0):
     """forward + backward of the reference algorithm on the host: per-Gaussian stages with
-    Jacobians, tile binning + sort, per-pixel compositing, its backward and the Jacobian chain,
-    rendering rows [476,604) of the 1080p view (a 1920x128 camera with cy shifted) of the
-    1M-Gaussian scene.  Returns (Mpix/s, sec/step, threads, dict with the scene)."""
+    Jacobians, tile binning + sort, per-pixel compositing, its backward and the Jacobian chain, on
+    the whole 1080p view of the 1M-Gaussian scene, OpenMP threads = os.cpu_count() whatever the
+    launcher exported.  Returns (Mpix/s, sec/step, threads, dict with the scene); `steps` timed
+    passes at most -- fewer once CPU_BUDGET_S is spent (the dict says how many)."""
     from oracle import oracle as orc
     from easygaussiansplatting_b200.scene import synthetic_scene, upstream_gradient
+    orc.set_num_threads(os.cpu_count() or 1)
     sc = synthetic_scene(N_GAUSS, WIDTH, HEIGHT, sh_dim=SH_DIM, seed=0)
     W, H = WIDTH, CROP_ROWS
     cy = sc["cy"] - CROP_Y0
     dl = upstream_gradient(WIDTH, HEIGHT, 0)[:, CROP_Y0:CROP_Y0 + CROP_ROWS, :].copy() * (3.0 * WIDTH * HEIGHT)
     f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32)
-    times = []
+    times, t_begin = [], time.perf_counter()
     for it in range(warmup + steps):
+        if times and time.perf_counter() - t_begin > CPU_BUDGET_S:
+            break
         t0 = time.perf_counter()
         us, pcs, depths, Ju = orc.project(sc["pws"], sc["Rcw"], sc["tcw"], sc["fx"], sc["fy"], sc["cx"], cy)
         d32 = f32(depths)
@@ -76,27 +87,39 @@ def cpu_sample(steps=1, warmup=0):
         if it >= warmup:
             times.append(dt)
     sec = statistics.median(times)
-    return W * H / sec / 1e6, sec, orc.num_threads(), dict(scene=sc, cy=cy, dl=dl)
+    return W * H / sec / 1e6, sec, orc.num_threads(), dict(scene=sc, cy=cy, dl=dl, passes=len(times))
 
 
-def sample_text(sec=None):
-    s = ("rows %d-%d of the 1920x1080 view (%dx%d px, %.1f%% of the frame), all 1M Gaussians, fwd+bwd"
-         % (CROP_Y0, CROP_Y0 + CROP_ROWS, WIDTH, CROP_ROWS, 100.0 * CROP_ROWS / HEIGHT))
+def sample_text(sec=None, passes=None):
+    s = "the whole 1920x1080 view, all 1M Gaussians, SH deg 3, fwd+bwd (same config as the GPU arm)"
+    if passes is not None:
+        s += ", %d timed pass%s" % (passes, "" if passes == 1 else "es")
     return s + (", %.1f s per pass" % sec if sec is not None else "")
+
+
+def config1_block():
+    """BASELINE config 1 (forward_cpu.py on 10k Gaussians, 256x256, SH deg 0) on this host."""
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "benchmarks"))
+        import config1_forward_cpu
+        return config1_forward_cpu.run(repeats=3, gpu=True)
+    except Exception as e:  # never let the side measurement take the bench line down
+        return {"error": repr(e)[:200]}
 
 
 def run_reference(args, rank):
     if rank != 0:
         return
-    mpix, sec, threads, _ = cpu_sample(steps=max(1, args.steps), warmup=min(1, args.warmup))
+    mpix, sec, threads, info = cpu_sample(steps=max(1, args.steps), warmup=min(1, args.warmup))
     line = {
         "impl": "reference", "metric": METRIC, "value": mpix, "unit": "Mpixels/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "config2: 1M synthetic Gaussians, 1920x1080, SH deg 3, fwd+bwd (CPU: bounded crop)",
+        "config": {"workload": "config2: 1M synthetic Gaussians, 1920x1080, SH deg 3, fwd+bwd",
                    "gaussians": N_GAUSS, "width": WIDTH, "height": HEIGHT, "sh_dim": SH_DIM},
+        "steps_timed": info["passes"],
         "cpu_baseline": {"value": mpix, "unit": "Mpixels/s", "cores": threads, "kind": "port",
-                         "sample": sample_text(sec)},
+                         "sample": sample_text(sec, info["passes"])},
         "e2e": {"value": mpix, "unit": "Mpixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -208,6 +231,19 @@ def run_ours(args, rank, world):
 
     step_fused, step_ops = make_step(GSFunctionFused, use_ex), make_step(GSFunction, False)
     step_fused_other = make_step(GSFunctionFused, not use_ex)   # the gradient sum done the other way
+    mv, mv_out = None, [None]
+    if world > 1:  # the selected multi-GPU step: factorised gradient sum (no autograd involved)
+        from easygaussiansplatting_b200.parallel import MultiViewStep
+        mv = MultiViewStep(params["pws"].detach(), params["rots"].detach(), params["scales"].detach(),
+                           params["shs"].detach(), alphas.detach())
+
+        def step_sel(dl):
+            image, ctx = mv.render(cam)
+            mv.backward(ctx, dl)
+            mv_out[0] = mv.reduce()
+            return image
+    else:
+        step_sel = step_fused
 
     copy_stream = torch.cuda.Stream(device=dev)
     ev_fwd, ev_dl = torch.cuda.Event(), torch.cuda.Event()
@@ -224,11 +260,15 @@ def run_ours(args, rank, world):
         with torch.cuda.stream(copy_stream):
             dl_dev.copy_(dl_host, non_blocking=True)
             ev_dl.record(copy_stream)
-        for p in leaves:
-            p.grad = None
-        cam.grad_exchange = exchange if use_ex else None
-        image, _ = GSFunctionFused.apply(params["pws"], params["shs"], alphas, params["scales"], params["rots"],
-                                         us0, cam)
+        ctx = None
+        if world > 1:
+            image, ctx = mv.render(cam)
+        else:
+            for p in leaves:
+                p.grad = None
+            cam.grad_exchange = None
+            image, _ = GSFunctionFused.apply(params["pws"], params["shs"], alphas, params["scales"], params["rots"],
+                                             us0, cam)
         ev_fwd.record(main)
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(ev_fwd)
@@ -236,10 +276,13 @@ def run_ours(args, rank, world):
             img.record_stream(copy_stream)
             img_host.copy_(img, non_blocking=True)
         main.wait_event(ev_dl)
-        image.backward(dl_dev)
-        if world > 1 and not use_ex:
-            allreduce_grads([p.grad for p in leaves])
-        chk_host.copy_(params["pws"].grad.abs().sum().reshape(1), non_blocking=True)
+        if world > 1:
+            mv.backward(ctx, dl_dev)
+            gp = mv.reduce()["dpws"]
+        else:
+            image.backward(dl_dev)
+            gp = params["pws"].grad
+        chk_host.copy_(gp.abs().sum().reshape(1), non_blocking=True)
         main.wait_stream(copy_stream)
 
     def timed(fn, steps, warmup, collective=True):
@@ -270,10 +313,10 @@ def run_ours(args, rank, world):
     if rank == 0:
         sampler.start()
     for _ in range(args.warmup):
-        step_fused(dl_dev)
+        step_sel(dl_dev)
     torch.cuda.synchronize()
     launches0 = lib.gsb_profile_launches(-1)
-    ms_dev = timed(lambda: step_fused(dl_dev), args.steps, 0)
+    ms_dev = timed(lambda: step_sel(dl_dev), args.steps, 0)
     launches = lib.gsb_profile_launches(-1) - launches0
     clocks = sampler.stop() if rank == 0 else None
     ms_e2e = timed(step_e2e, args.steps, max(3, args.warmup // 2))
@@ -285,7 +328,7 @@ def run_ours(args, rank, world):
     e2e = pix * args.steps / (ms_e2e * 1e-3) / 1e6
 
     allreduce = None
-    if world > 1:  # the two ways of summing the gradients, against each other
+    if world > 1:  # the three ways of summing the gradients, against each other
         nccl_step = step_fused_other if use_ex else step_fused
         ex_step = step_fused if use_ex else step_fused_other
         nccl_step(dl_dev)
@@ -293,25 +336,31 @@ def run_ours(args, rank, world):
         ms_ar = timed(lambda: allreduce_grads([p.grad for p in leaves]), 10, 3)   # grads = flat bucket views
         nbytes = allreduce_grads([p.grad for p in leaves])
         n_other = max(5, args.steps // 2)
-        ms_other = timed(lambda: step_fused_other(dl_dev), n_other, 2) / n_other
+        ms_nccl = timed(lambda: nccl_step(dl_dev), n_other, 2) / n_other
+        ms_ex = timed(lambda: ex_step(dl_dev), n_other, 2) / n_other
         ex_step(dl_dev)
         torch.cuda.synchronize()
         diff = max(float((p.grad - g).abs().max() / g.abs().max().clamp_min(1e-30)) for p, g in zip(leaves, ref_grads))
-        ms_this = ms_dev / args.steps
-        allreduce = {"bytes": int(nbytes), "ms": ms_ar / 10,
-                     "algbw_GBps": nbytes / (ms_ar / 10 * 1e-3) / 1e9,
-                     "what": "`ms`: NCCL all-reduce of the flat 236 B/Gaussian gradient bucket alone.  The step is "
-                             "timed with both gradient sums; `value` uses `selected`",
-                     "selected": "fused_exchange" if use_ex else "nccl_allreduce",
-                     "step_ms_with_nccl_allreduce": ms_other if use_ex else ms_this,
-                     "step_ms_with_fused_exchange": ms_this if use_ex else ms_other,
+        step_sel(dl_dev)
+        torch.cuda.synchronize()
+        g = mv_out[0]
+        fact = [g["dpws"], g["dshs"], g["dalphas"].reshape(-1, 1), g["dscales"], g["drots"]]
+        diff_f = max(float((a - b).abs().max() / b.abs().max().clamp_min(1e-30)) for a, b in zip(fact, ref_grads))
+        allreduce = {"selected": "factorised (all-reduce 44 B + all-gather 12 B/view per Gaussian, local dL/dsh "
+                                 "expansion; parallel.MultiViewStep)",
+                     "factorised_bytes_per_rank": g["bytes_per_rank"], "flat_bucket_bytes": int(nbytes),
+                     "step_ms_factorised": ms_dev / args.steps,
+                     "step_ms_with_nccl_allreduce": ms_nccl, "step_ms_with_fused_exchange": ms_ex,
+                     "nccl_flat_allreduce_alone_ms": ms_ar / 10,
+                     "nccl_flat_allreduce_algbw_GBps": nbytes / (ms_ar / 10 * 1e-3) / 1e9,
+                     "factorised_vs_nccl_max_rel_diff": diff_f,
                      "exchange_vs_nccl_max_rel_diff": diff, "exchange_status": exchange.status()}
 
     # ---- per-kernel durations with CUDA events on the launch stream (roofline leg)
     prof_steps = 5
     lib.gsb_profile_enable(1)
     for _ in range(prof_steps):
-        step_fused(dl_dev)
+        step_sel(dl_dev)
     torch.cuda.synchronize()
     lib.gsb_profile_enable(0)
     kern = {}
@@ -320,6 +369,7 @@ def run_ours(args, rank, world):
         lib.gsb_profile_read(i, C.byref(ms_tot), C.byref(cnt))
         if cnt.value:
             kern[lib.gsb_profile_kernel_name(i).decode()] = ms_tot.value / prof_steps
+    config5 = run_config5(torch, dist, dev, rank, world, timed)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -345,7 +395,7 @@ def run_ours(args, rank, world):
     peak, peak_src = peaks()
     achieved = alg[roof_k] / (kern[roof_k] * 1e-3) / 1e9
     traffic, traffic_src = None, None   # dram__bytes_read + write per launch from the committed ncu capture
-    tpath = os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r2_ncu_traffic.json")
     if os.path.exists(tpath):
         tj = json.load(open(tpath))
         traffic, traffic_src = tj.get(roof_k), tj.get("source")
@@ -423,7 +473,11 @@ def run_ours(args, rank, world):
                  "vs_reference": "profiles/r1_compare_density_ref.json (same inputs through the reference's gsmodel.py)"}
     del dP, dM, dV
 
-    # ---- CPU baseline + gradient error vs the CPU oracle on the same crop
+    # ---- the reference's own CUDA extension on the same GPU, same harness (when it was built
+    # into baseline/_ref by baseline/build_ref_gpu.sh): its own process -- both modules are `gsplatcu`
+    ref_gpu = reference_gpu_block(local)
+
+    # ---- CPU baseline + gradient error vs the CPU oracle on the same frame
     cpu_mpix, cpu_sec, cpu_threads, cpu = cpu_sample(steps=1, warmup=0)
     err = gpu_vs_cpu_crop(torch, dev, cpu)
     line = {
@@ -434,10 +488,9 @@ def run_ours(args, rank, world):
                                "parameter gradients (fused preprocess fwd/bwd + splat + splatB)",
                    "gaussians": N_GAUSS, "width": WIDTH, "height": HEIGHT, "sh_dim": SH_DIM, "patches": P,
                    "p_eff": p_eff, "views_per_step": world,
-                   "parallelism": ("1 view/rank, shared Gaussians; parameter gradients summed by " +
-                                   ("the fused peer-memory exchange (push from the backward kernel + reduce/"
-                                    "broadcast kernel)" if use_ex else "an NCCL all-reduce of the flat bucket")
-                                   if world > 1 else "single GPU"),
+                   "parallelism": ("1 view/rank, shared Gaussians; parameter gradients summed by the factorised "
+                                   "exchange (NCCL all-reduce of 11 floats + all-gather of every view's dL/dcolor, "
+                                   "dL/dsh expanded locally)" if world > 1 else "single GPU"),
                    "l2": "per-step working set (params+grads 0.47 GB, records 0.12 GB, sort buffers) > 126 MB L2; "
                          "no explicit flush"},
         "gaussians_per_s": N_GAUSS * world * args.steps / (ms_dev * 1e-3),
@@ -452,7 +505,8 @@ def run_ours(args, rank, world):
         "loss_n2": loss_info,
         "density_n3": dens_info,
         "cpu_baseline": {"value": cpu_mpix, "unit": "Mpixels/s", "cores": cpu_threads, "kind": "port",
-                         "sample": sample_text(cpu_sec)},
+                         "sample": sample_text(cpu_sec, cpu["passes"]), "config1": config1_block()},
+        "ref_gpu": ref_gpu,
         "e2e": {"value": e2e, "unit": "Mpixels/s", "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": int(dl_host.numel() * 4 + cam_host.numel() * 4),
                 "d2h_bytes_per_step": int(img_host.numel() * 4 + 4),
@@ -460,6 +514,7 @@ def run_ours(args, rank, world):
         "gpu_launches": int(launches),
         "clocks": clocks,
     }
+    line["config5"] = config5
     if allreduce is not None:
         line["allreduce"] = allreduce
     print(json.dumps(line))
@@ -467,8 +522,79 @@ def run_ours(args, rank, world):
         dist.destroy_process_group()
 
 
+def run_config5(torch, dist, dev, rank, world, timed):
+    """BASELINE config 5 as written: 2M shared Gaussians, 8 cameras per step on a ring, split over
+    the ranks (8 / world views each, gradients accumulated locally), ONE factorised exchange per
+    step.  Strong scaling in the ranks: the work per step is fixed.  Every rank runs it; rank 0
+    reports.  world = 1: the 8 views in sequence, no exchange."""
+    from easygaussiansplatting_b200.gsfunction import Camera
+    from easygaussiansplatting_b200.parallel import MultiViewStep
+    from easygaussiansplatting_b200.scene import ring_camera, synthetic_scene, upstream_gradient
+    N5, V5 = 2_000_000, 8
+    if V5 % world != 0:
+        return {"skipped": "8 cameras do not split over %d ranks" % world}
+    sc = synthetic_scene(N5, WIDTH, HEIGHT, sh_dim=SH_DIM, seed=1)
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    mv = MultiViewStep(T(sc["pws"]), T(sc["rots"]), T(sc["scales"]), T(sc["shs"]), T(sc["alphas"][:, None]))
+    mine = [v for v in range(V5) if v % world == rank]
+    cams = []
+    for v in mine:
+        Rcw, tcw, twc = ring_camera(v, V5)
+        cams.append(Camera(WIDTH, HEIGHT, sc["fx"], sc["fy"], sc["cx"], sc["cy"], T(Rcw), T(tcw), T(twc)))
+    dl = T(upstream_gradient(WIDTH, HEIGHT, rank) * (3.0 * WIDTH * HEIGHT))
+    out = [None]
+
+    def step():
+        for cam in cams:
+            image, ctx = mv.render(cam)
+            mv.backward(ctx, dl)
+        out[0] = mv.reduce()
+    n = 5
+    ms = timed(step, n, 3) / n
+    res = {"what": "config 5: 2M shared Gaussians, 8 cameras/step at 1920x1080, %d view(s) per rank, one "
+                   "factorised gradient exchange per step (strong scaling over the ranks)" % len(mine),
+           "gaussians": N5, "views_per_step": V5, "n_gpus": world, "ms_per_step": ms,
+           "value": V5 * WIDTH * HEIGHT / (ms * 1e-3) / 1e6, "unit": "Mpixels/s", "scaling": "strong",
+           "exchange_bytes_per_rank": out[0]["bytes_per_rank"] if world > 1 else 0}
+    del mv, out
+    torch.cuda.empty_cache()
+    return res
+
+
+def reference_gpu_block(gpu_index):
+    """t_fwd / t_bwd of the UNMODIFIED reference `gsplatcu` (baseline/_ref/gsplatcu*.so) through the
+    same autograd wrapper on config 2, with the same clock sampler (benchmarks/compare_ref_gpu.py
+    --arm ref).  None when the extension is not installed."""
+    ref_dir = os.path.join(ROOT, "baseline", "_ref")
+    if not (os.path.isdir(ref_dir) and any(f.startswith("gsplatcu") and f.endswith(".so") for f in os.listdir(ref_dir))):
+        return None
+    out = os.path.join(ROOT, "gpurun_out", "bench_ref_gpu")
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    sampler = ClockSampler(gpu_index)
+    sampler.start()
+    try:
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "benchmarks", "compare_ref_gpu.py"), "--arm", "ref",
+                            "--iters", "10", "--out", out, "--configs", "config2"],
+                           capture_output=True, text=True, timeout=600)
+        clocks = sampler.stop()
+        if r.returncode != 0:
+            return {"error": r.stderr[-300:]}
+        res = json.load(open(out + ".ref.json"))["config2"]
+        for f in os.listdir(os.path.dirname(out)):  # the arm's raw tensors are scratch
+            if f.startswith("bench_ref_gpu.ref.json.") and f.endswith(".npz"):
+                os.remove(os.path.join(os.path.dirname(out), f))
+        return {"what": "the reference's own gsplatcu (unmodified, built for sm_100a) on this GPU: GSFunction.apply "
+                        "(6 ops, calc_J=True) + image.backward (splatB + torch Jacobian chain), config 2, CUDA "
+                        "events, median of 10",
+                "t_fwd_ms": res["t_fwd_ms"], "t_bwd_ms": res["t_bwd_ms"], "splat_ms": res["splat_ms"],
+                "splatB_ms": res["splatB_ms"], "value": res["mpix_per_s"], "unit": "Mpixels/s", "clocks": clocks}
+    except Exception as e:
+        sampler.stop()
+        return {"error": repr(e)[:300]}
+
+
 def gpu_vs_cpu_crop(torch, dev, cpu):
-    """GPU vs CPU oracle on the CPU-sample crop (1920x128 view of the 1M scene).
+    """GPU vs CPU oracle on the CPU arm's frame (the whole 1920x1080 view of the 1M scene).
     splat / splatB are compared on the GPU's own fp32 op inputs (what the operator actually
     received); Gaussians whose alpha' comes within 2e-5 of the 0.002 threshold at some pixel are
     reported separately (an fp32 kernel may take the other branch there).  The per-Gaussian

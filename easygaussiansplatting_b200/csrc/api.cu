@@ -38,7 +38,7 @@ static const char *const g_names[K_COUNT] = {"project", "computeCov3D", "compute
                                              "small_bmm", "density_accumulate", "density_classify",
                                              "density_scan(cub)", "density_apply", "reset_alpha",
                                              "ply_rows_to_gs", "gs_to_params", "params_to_gs",
-                                             "grad_reduce_broadcast"};
+                                             "grad_reduce_broadcast", "sh_grad_expand"};
 
 ProfScope::ProfScope(int id, cudaStream_t st) : id_(id), st_(st), stop_(nullptr) {
   std::lock_guard<std::mutex> lk(g_prof_mu);
@@ -179,8 +179,8 @@ int gsb_preprocess_backward(int N, int sh_dim3, const float *pws, const float *r
     GSB_REQUIRE(sh_dim3 == 1 || sh_dim3 == 4 || sh_dim3 == 9 || sh_dim3 == 16,
                 "preprocessB: shs.shape[1]/3 must be 1, 4, 9 or 16");
     GSB_REQUIRE(N == 0 || (pws && rots && scales && shs && Rcw && tcw && twc && cinv2ds && dloss_dus_out &&
-                           dloss_dalphas_out && dloss_dpws && dloss_dshs && dloss_dscales && dloss_drots),
-                "preprocessB: null pointer");
+                           dloss_dalphas_out && dloss_dpws && dloss_dscales && dloss_drots),
+                "preprocessB: null pointer");  // (dloss_dshs may be NULL: see gsb_sh_grad_expand)
     const MomentsIn mi{moments, cinv2ds, dloss_dus_out, dloss_dalphas_out};
     return launch_preprocess_bwd(N, sh_dim3, pws, rots, scales, shs, Rcw, tcw, twc, fx, fy, cx, cy, width, height,
                                  nullptr, nullptr, nullptr, dloss_dpws, dloss_dshs, dloss_dscales, dloss_drots, &mi,
@@ -194,6 +194,15 @@ int gsb_preprocess_backward(int N, int sh_dim3, const float *pws, const float *r
   return launch_preprocess_bwd(N, sh_dim3, pws, rots, scales, shs, Rcw, tcw, twc, fx, fy, cx, cy, width, height,
                                dloss_dus, dloss_dcinv2ds, dloss_dcolors, dloss_dpws, dloss_dshs, dloss_dscales,
                                dloss_drots, nullptr, (cudaStream_t)stream);
+}
+
+int gsb_sh_grad_expand(int N, int sh_dim3, int V, const float *pws, const float *twcs, const float *dloss_dcolors,
+                       float *dloss_dshs, gsb_stream_t stream) {
+  GSB_REQUIRE(N >= 0 && V >= 1, "sh_grad_expand: bad N / V");
+  GSB_REQUIRE(sh_dim3 == 1 || sh_dim3 == 4 || sh_dim3 == 9 || sh_dim3 == 16,
+              "sh_grad_expand: sh_dim3 must be 1, 4, 9 or 16");
+  GSB_REQUIRE(N == 0 || (pws && twcs && dloss_dcolors && dloss_dshs), "sh_grad_expand: null pointer");
+  return launch_sh_expand(N, sh_dim3, V, pws, twcs, dloss_dcolors, dloss_dshs, (cudaStream_t)stream);
 }
 
 int gsb_small_bmm(long long batch, int m, int k, int n, const float *A, const float *B, int b_shared, float *C,
@@ -278,8 +287,10 @@ int gsb_splat_render(int H, int W, int N, int64_t P, uint32_t depth_key_max, con
   }
   // sparse frame (< 48 patches per tile on average): persistent grid + tile queue
   const int64_t T = (int64_t)((W + GSB_TILE - 1) / GSB_TILE) * ((H + GSB_TILE - 1) / GSB_TILE);
+  int *const work_counter = tile_counter;
   if (P >= 48 * T) tile_counter = nullptr;
-  return launch_draw(H, W, patch_range_per_tile, recs, gsid_per_patch, image, contrib, final_tau, tile_counter, st);
+  return launch_draw(H, W, patch_range_per_tile, recs, gsid_per_patch, image, contrib, final_tau, tile_counter,
+                     work_counter, st);
 }
 
 int gsb_splat_forward(int H, int W, int N, const float *us, const float *cinv2ds, const float *alphas,
@@ -310,7 +321,7 @@ int gsb_splat_forward(int H, int W, int N, const float *us, const float *cinv2ds
     GSB_CUDA_TRY(cudaMemsetAsync(patch_range_per_tile, 0,
                                  sizeof(int32_t) * 2 * (size_t)((W + GSB_TILE - 1) / GSB_TILE) * ((H + GSB_TILE - 1) / GSB_TILE), st));
     return launch_draw(H, W, patch_range_per_tile, nullptr, gsid_per_patch, image, contrib, final_tau,
-                       static_cast<int *>(ws), st);
+                       static_cast<int *>(ws), static_cast<int *>(ws), st);
   }
   rc = launch_sort_and_pack(H, W, N, P_cap, depth_key_cap, us, cinv2ds, alphas, depths, colors, bin_ws, BL, ws, SL,
                             patch_range_per_tile, gsid_per_patch, packed_records == nullptr, &sr, st);
@@ -320,8 +331,10 @@ int gsb_splat_forward(int H, int W, int N, const float *us, const float *cinv2ds
   // sparse frame -> persistent tile queue; the host does not know P yet, the capacity stands in
   int *tile_counter = reinterpret_cast<int *>(static_cast<char *>(ws) + SL.counters);
   const int64_t T = (int64_t)((W + GSB_TILE - 1) / GSB_TILE) * ((H + GSB_TILE - 1) / GSB_TILE);
+  int *const work_counter = tile_counter;
   if (P_cap >= 60 * T) tile_counter = nullptr;
-  rc = launch_draw(H, W, patch_range_per_tile, recs, gsid_per_patch, image, contrib, final_tau, tile_counter, st);
+  rc = launch_draw(H, W, patch_range_per_tile, recs, gsid_per_patch, image, contrib, final_tau, tile_counter,
+                   work_counter, st);
   if (rc) return rc;
   // the sort and the rasterizer are queued; now look at what the binning found
   GSB_CUDA_TRY(cudaEventSynchronize(ready));

@@ -13,12 +13,17 @@
 //
 // Traffic per rank: (world-1)/world of the 236 B/Gaussian bucket out in each phase, the same as
 // a ring all-reduce, but phase 1 rides under the backward kernel and nothing is staged twice.
-// Flags are monotonically increasing epochs (no reset race); every spin has a 5 s timeout that
-// sets the region's status word instead of hanging the GPU if a peer died.
+// Flags are monotonically increasing epochs (no reset race).  Every spin has a timeout
+// (GSB_EXCHANGE_TIMEOUT_S, default 120 s: rank skew from a checkpoint, an evaluation pass or a lazy
+// module load is normal) after which the region's sticky status word is set and the rows this
+// rank owns are POISONED with NaN in every rank's result, so a lost peer can never pass for a
+// finished sum; GradExchange.status() / the next host call reports it.
 //
 // Peer mapping is plain CUDA IPC (cudaIpcGetMemHandle / cudaIpcOpenMemHandle) on cudaMalloc'd
 // regions owned by this library; the 64-byte handles travel between the processes through
 // torch.distributed (parallel.py) -- plumbing, not data path.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "kernels.h"
 #include "tile_io.cuh"
@@ -59,17 +64,19 @@ struct ReduceArgs {
   const uint32_t *arrive;      // local arrive[]
   const uint32_t *done_local;  // local done[]
   uint32_t *counter, *status;
+  unsigned long long timeout_ns;
   long long rpr, slot_floats, slot_off[5], result_off[5];
   int seg_k[5];
   int world, rank;
   uint32_t epoch;
 };
 
-__device__ __forceinline__ bool wait_flags(const uint32_t *flags, int world, uint32_t epoch, uint32_t *status) {
+__device__ __forceinline__ bool wait_flags(const uint32_t *flags, int world, uint32_t epoch, uint32_t *status,
+                                           unsigned long long timeout_ns) {
   const unsigned long long t0 = globaltimer_ns();
   for (int s = 0; s < world; s++) {
     while ((int)(ld_acquire_sys(flags + s) - epoch) < 0) {
-      if (globaltimer_ns() - t0 > 5000000000ull) {  // a peer never arrived: report, do not hang
+      if (globaltimer_ns() - t0 > timeout_ns) {  // a peer never arrived: report, do not hang
         atomicExch(status, 1u);
         return false;
       }
@@ -82,18 +89,22 @@ __device__ __forceinline__ bool wait_flags(const uint32_t *flags, int world, uin
 template <int WORLD>
 __global__ void __launch_bounds__(256) k_grad_reduce_bcast(ReduceArgs a) {
   __shared__ int ok;
-  if (threadIdx.x == 0) ok = wait_flags(a.arrive, WORLD, a.epoch, a.status);
+  if (threadIdx.x == 0) ok = wait_flags(a.arrive, WORLD, a.epoch, a.status, a.timeout_ns) && *a.status == 0;
   __syncthreads();
-  if (ok) {
+  {
     const float4 *st4 = reinterpret_cast<const float4 *>(a.staging);
     const long long slot4 = a.slot_floats / 4;
     const long long stride = (long long)gridDim.x * blockDim.x;
+    const float nan = __int_as_float(0x7fc00000);
     for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < slot4; v += stride) {
-      float4 acc = st4[v];
+      float4 acc = make_float4(nan, nan, nan, nan);  // a timed-out exchange poisons its rows
+      if (ok) {
+        acc = st4[v];
 #pragma unroll
-      for (int s = 1; s < WORLD; s++) {
-        const float4 x = st4[s * slot4 + v];
-        acc.x += x.x, acc.y += x.y, acc.z += x.z, acc.w += x.w;
+        for (int s = 1; s < WORLD; s++) {
+          const float4 x = st4[s * slot4 + v];
+          acc.x += x.x, acc.y += x.y, acc.z += x.z, acc.w += x.w;
+        }
       }
       // float offset inside the slot -> segment -> local tile -> global tile lt * world + rank
       // (tiles are dealt round-robin; a tile is 128 * K floats, a multiple of 4, so a float4
@@ -118,7 +129,7 @@ __global__ void __launch_bounds__(256) k_grad_reduce_bcast(ReduceArgs a) {
       *a.counter = 0;
       __threadfence_system();
       for (int p = 0; p < WORLD; p++) st_release_sys(a.done[p] + a.rank, a.epoch);
-      wait_flags(a.done_local, WORLD, a.epoch, a.status);
+      wait_flags(a.done_local, WORLD, a.epoch, a.status, a.timeout_ns);
     }
   }
 }
@@ -149,8 +160,17 @@ int launch_grad_reduce_bcast(const ExchangeGeom &G, int rank, void *const *regio
   a.world = G.world;
   a.rank = rank;
   a.epoch = epoch;
+  static const unsigned long long timeout_ns = [] {
+    const char *e = getenv("GSB_EXCHANGE_TIMEOUT_S");
+    const double sec = e != nullptr ? atof(e) : 120.0;
+    return (unsigned long long)((sec > 0.001 ? sec : 0.001) * 1e9);
+  }();
+  a.timeout_ns = timeout_ns;
   ProfScope ps(K_GRAD_EXCHANGE, st);
-  const int grid = 148 * 4;
+  int dev = 0, sms = 148;  // (per current device: ranks of one process may sit on different GPUs)
+  GSB_CUDA_TRY(cudaGetDevice(&dev));
+  GSB_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int grid = sms * 4;
   switch (G.world) {
     case 1: k_grad_reduce_bcast<1><<<grid, 256, 0, st>>>(a); break;
     case 2: k_grad_reduce_bcast<2><<<grid, 256, 0, st>>>(a); break;

@@ -157,7 +157,9 @@ __global__ void __launch_bounds__(PG) k_preprocess_bwd(
     g_scales = sb + gp.off_scales;
     if (valid) (sb + gp.off_alphas)[drow + tid] = MOM ? galpha : __ldg(gp.g_alphas + base + tid);
   }
-  tile_flush<KS>(g_shs, drow, nv, sm, tid);
+  // g_shs == nullptr: the caller re-expands dL/dsh = sum over views of Y(dir_v) (x) dL/dcolor_v itself
+  // (multi-view data parallel: 12 B/view travel instead of the 192 B row, k_sh_expand below)
+  if (g_shs != nullptr) tile_flush<KS>(g_shs, drow, nv, sm, tid);
   if (valid) {  // the 10 small gradient floats: direct strided stores (no staging, no barriers)
     const long long o = drow + tid;
     g_pws[3 * o] = gpw[0]; g_pws[3 * o + 1] = gpw[1]; g_pws[3 * o + 2] = gpw[2];
@@ -182,6 +184,56 @@ __global__ void __launch_bounds__(PG) k_preprocess_bwd(
   }
 }
 
+// dL/dsh of one Gaussian summed over V views from the views' dL/dcolor:
+//   colour = 0.5 + sum_l Y_l(dir) sh_l is linear in sh and never clamped (kernel.cu:735-774), so
+//   dL/dsh[l][c] = sum_v Y_l(dir_v) dL/dcolor_v[c]   with dir_v = (pw - twc_v) / |pw - twc_v|,
+// the same Y (same instruction sequence) as backward_one evaluates; for V = 1 the result is
+// bit-identical to the dL/dsh row the per-Gaussian backward writes.  Multi-view data parallel
+// training exchanges the 12-byte dL/dcolor per view instead of the 192-byte dL/dsh row and
+// expands on every rank (parallel.MultiViewStep).  Views are summed in index order.
+template <int K3>
+__global__ void __launch_bounds__(PG) k_sh_expand(int N, int V, const float *__restrict__ pws,
+                                                  const float *__restrict__ twcs, const float *__restrict__ gcols,
+                                                  float *__restrict__ g_shs) {
+  constexpr int KS = 3 * K3;
+  __shared__ float sm[TileT<KS>::FLOATS];
+  const int tid = threadIdx.x;
+  const long long base = (long long)blockIdx.x * PG;
+  const int nv = min(PG, (int)(N - base));
+  const bool valid = tid < nv;
+  float acc[KS];
+#pragma unroll
+  for (int i = 0; i < KS; i++) acc[i] = 0.f;
+  if (valid) {
+    const long long i = base + tid;
+    const float pw[3] = {__ldg(pws + 3 * i), __ldg(pws + 3 * i + 1), __ldg(pws + 3 * i + 2)};
+    for (int v = 0; v < V; v++) {
+      const float *gc = gcols + ((size_t)v * N + i) * 3;
+      const float g0 = __ldg(gc), g1 = __ldg(gc + 1), g2 = __ldg(gc + 2);
+      float Y[K3], dY[K3][3];
+      float r[3] = {0.f, 0.f, 0.f};
+      if (K3 > 1) {
+        const float d0 = pw[0] - __ldg(twcs + 3 * v), d1 = pw[1] - __ldg(twcs + 3 * v + 1),
+                    d2 = pw[2] - __ldg(twcs + 3 * v + 2);
+        const float ninv = 1.0f / sqrtf(d0 * d0 + d1 * d1 + d2 * d2);
+        r[0] = d0 * ninv; r[1] = d1 * ninv; r[2] = d2 * ninv;
+      }
+      pg::sh_basis<K3>(r[0], r[1], r[2], Y, dY);
+#pragma unroll
+      for (int l = 0; l < K3; l++) {
+        acc[3 * l] += g0 * Y[l];
+        acc[3 * l + 1] += g1 * Y[l];
+        acc[3 * l + 2] += g2 * Y[l];
+      }
+    }
+    float *row = ROWK(KS);
+#pragma unroll
+    for (int e = 0; e < KS; e++) row[e] = acc[e];
+  }
+  __syncthreads();
+  tile_flush<KS>(g_shs, base, nv, sm, tid);
+}
+
 #define GSB_DISPATCH_K3(k3, CALL)                                           \
   switch (k3) {                                                             \
     case 1: { constexpr int K3 = 1; CALL; } break;                          \
@@ -203,6 +255,16 @@ int launch_preprocess_fwd(int N, int k3, const float *pws, const float *rots, co
   GSB_DISPATCH_K3(k3, (k_preprocess_fwd<K3><<<nb, PG, 0, st>>>(N, pws, rots, scales, shs, Rcw, tcw, twc, fx, fy, cx,
                                                                 cy, tfx, tfy, us, cinv2ds, colors, depths, areas,
                                                                 alphas, recs)));
+  GSB_CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int launch_sh_expand(int N, int k3, int V, const float *pws, const float *twcs, const float *gcols, float *g_shs,
+                     cudaStream_t st) {
+  if (N <= 0) return 0;
+  const int nb = (N + PG - 1) / PG;
+  ProfScope ps(K_SH_EXPAND, st);
+  GSB_DISPATCH_K3(k3, (k_sh_expand<K3><<<nb, PG, 0, st>>>(N, V, pws, twcs, gcols, g_shs)));
   GSB_CUDA_TRY(cudaGetLastError());
   return 0;
 }

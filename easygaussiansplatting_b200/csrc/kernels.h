@@ -15,7 +15,7 @@ enum KernelId {
   K_PROJECT = 0, K_COV3D, K_COV2D, K_SH2COLOR, K_INVCOV, K_RECTS, K_SCAN, K_KEYS, K_SORT, K_RANGES,
   K_PACK, K_DRAW, K_DRAW_BWD, K_PRE_FWD, K_PRE_BWD, K_FINALIZE, K_LOSS_FWD, K_LOSS_BWD, K_BMM,
   K_DENSITY_ACC, K_DENSITY_CLASSIFY, K_DENSITY_SCAN, K_DENSITY_APPLY, K_RESET_ALPHA, K_GS_DECODE,
-  K_GS_TO_PARAMS, K_PARAMS_TO_GS, K_GRAD_EXCHANGE, K_COUNT
+  K_GS_TO_PARAMS, K_PARAMS_TO_GS, K_GRAD_EXCHANGE, K_SH_EXPAND, K_COUNT
 };
 struct ProfScope {
   ProfScope(int id, cudaStream_t st);
@@ -56,6 +56,10 @@ int launch_preprocess_bwd(int N, int k3, const float *pws, const float *rots, co
                           float fy, float cx, float cy, float width, float height, const float *g_us,
                           const float *g_cinv2ds, const float *g_colors, float *g_pws, float *g_shs,
                           float *g_scales, float *g_rots, const MomentsIn *mi, cudaStream_t st);
+
+// dL/dsh[N,3k] = sum over V views of Y(dir_v) (x) dL/dcolor_v  (fused.cu k_sh_expand)
+int launch_sh_expand(int N, int k3, int V, const float *pws, const float *twcs, const float *gcols, float *g_shs,
+                     cudaStream_t st);
 
 // ---- multi-GPU gradient exchange (comm.cu; the producer is the PUSH variant in fused.cu).
 // Every rank owns one region of peer-mapped memory:
@@ -156,7 +160,9 @@ int launch_draw_bwd4_kernel(int H, int W, const int32_t *ranges, const Rec *recs
                             const int32_t *contrib, const float *final_tau, const float *dloss_dgammas,
                             float *moments, int *work_counter, cudaStream_t st);
 int launch_draw(int H, int W, const int32_t *ranges, const Rec *recs, const int32_t *gsid, float *image,
-                int32_t *contrib, float *final_tau, int *tile_counter, cudaStream_t st);
+                int32_t *contrib, float *final_tau, int *tile_counter, int *work_counter, cudaStream_t st);
+int launch_draw3(int H, int W, const int32_t *ranges, const Rec *recs, const int32_t *gsid, float *image,
+                 int32_t *contrib, float *final_tau, int *work_counter, cudaStream_t st);
 int launch_draw_backward(int H, int W, int N, const int32_t *ranges, const Rec *recs, const int32_t *gsid,
                          const int32_t *contrib,
                          const float *final_tau, const float *dloss_dgammas, const float *cinv2ds,

@@ -16,6 +16,8 @@
 // by a gather -- thread t takes the t-th Gaussian id of the batch from the sorted patch list and
 // issues three 16-byte cp.async tracked by the stage's mbarrier (common.cuh gather_record).
 // Warp-level exact culling (rec_can_touch) drops records that cannot reach the warp's 8x8 block.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -189,20 +191,24 @@ __global__ void __launch_bounds__(128) k_draw2(int W, int H, int gx, int T, cons
 }
 
 int persistent_grid(int T, int ctas_per_sm) {
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
-  }
+  int dev = 0, sms = 148;  // queried per call: per current device, thread-safe
+  if (cudaGetDevice(&dev) != cudaSuccess ||
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
+    sms = 148;
   const long long g = (long long)sms * ctas_per_sm;
   return (int)(T < g ? T : g);
 }
 
 int launch_draw(int H, int W, const int32_t *ranges, const Rec *recs, const int32_t *gsid, float *image,
-                 int32_t *contrib, float *final_tau, int *tile_counter, cudaStream_t st) {
+                 int32_t *contrib, float *final_tau, int *tile_counter, int *work_counter, cudaStream_t st) {
   const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
   if (gx <= 0 || gy <= 0) return 0;
+  // GSB_FWD_VARIANT=2 selects this file's CTA-per-tile kernel for A/B runs; default: raster_fwd3.cu
+  static const int variant = [] {
+    const char *e = getenv("GSB_FWD_VARIANT");
+    return e != nullptr ? atoi(e) : 3;
+  }();
+  if (variant != 2) return launch_draw3(H, W, ranges, recs, gsid, image, contrib, final_tau, work_counter, st);
   const int T = gx * gy;
   if (tile_counter != nullptr) GSB_CUDA_TRY(cudaMemsetAsync(tile_counter, 0, sizeof(int), st));
   ProfScope ps(K_DRAW, st);

@@ -127,8 +127,10 @@ class GSFunctionFused(torch.autograd.Function):
             # its tiles into peer memory and the gradients come back already summed over ranks
             # (dloss_dus stays this view's own: it only feeds the densification statistics)
             g = ex.backward(pws, rots, scales, shs, cam, moments=moments, cinv2ds=cinv2ds)
-            return (g["dpws"], g["dshs"], g["dalphas"].reshape(ctx.alpha_shape), g["dscales"], g["drots"],
-                    g["dus"], None)
+            # the result region is overwritten by the next step's broadcast: hand autograd its own
+            # copies (AccumulateGrad may keep a returned tensor, and so may hooks / retain_grad)
+            return (g["dpws"].clone(), g["dshs"].clone(), g["dalphas"].clone().reshape(ctx.alpha_shape),
+                    g["dscales"].clone(), g["drots"].clone(), g["dus"], None)
         dpws, dshs, dscales, drots, dloss_dus, dloss_dalphas = ops.preprocessB(
             pws, rots, scales, shs, cam.Rcw, cam.tcw, cam.twc, cam.fx, cam.fy, cam.cx, cam.cy,
             cam.width, cam.height, None, None, None, moments=moments, cinv2ds=cinv2ds)

@@ -384,12 +384,15 @@ def preprocess(pws, rots, scales, shs, Rcw, tcw, twc, focal_x, focal_y, center_x
 
 
 def preprocessB(pws, rots, scales, shs, Rcw, tcw, twc, focal_x, focal_y, center_x, center_y, width, height,
-                dloss_dus, dloss_dcinv2ds, dloss_dcolors, moments=None, cinv2ds=None):
+                dloss_dus, dloss_dcinv2ds, dloss_dcolors, moments=None, cinv2ds=None, compact=False):
     """Vector-Jacobian products of the five per-Gaussian stages (== the torch.bmm chain of
     gsmodel.py:72-85).  -> [dloss_dpws[N,3], dloss_dshs[N,3k], dloss_dscales[N,3], dloss_drots[N,4]]
     With moments[N,9] (from `splatB(..., moments_only=True)`) and the forward's cinv2ds[N,3] the
     three dloss_d* arguments are ignored (pass None) and two more outputs follow:
-    dloss_dus[N,2], dloss_dalphas[N]."""
+    dloss_dus[N,2], dloss_dalphas[N].
+    compact (with moments): dloss_dshs is not produced (None) -- the caller expands it from the
+    views' dL/dcolor = moments[:, 6:9] with `sh_grad_expand` -- and the other gradients share one
+    flat bucket [dpws | dscales | drots | dalphas] of 11 N floats (one collective sums it)."""
     pws = _chk(pws, "pws", last=3, ndim=2); rots = _chk(rots, "rots", last=4, ndim=2)
     scales = _chk(scales, "scales", last=3, ndim=2); shs = _chk(shs, "shs", ndim=2)
     Rcw = _chk(Rcw, "Rcw"); tcw = _chk(tcw, "tcw"); twc = _chk(twc, "twc")
@@ -416,13 +419,23 @@ def preprocessB(pws, rots, scales, shs, Rcw, tcw, twc, focal_x, focal_y, center_
     # gradients in place with a single collective (parallel.allreduce_grads); every view starts
     # 16-byte aligned (3k*N and 4*N floats are multiples of 4 elements when N % 4 == 0; the
     # kernels fall back to scalar stores otherwise)
-    bucket = torch.empty((N * (3 * k + 10),), **o)
-    gsh = bucket[:N * 3 * k].view(N, 3 * k)
-    gq = bucket[N * 3 * k:N * (3 * k + 4)].view(N, 4)
-    gpw = bucket[N * (3 * k + 4):N * (3 * k + 7)].view(N, 3)
-    gs = bucket[N * (3 * k + 7):].view(N, 3)
+    if compact:
+        if moments is None:
+            raise ValueError("compact=True needs the moment rows")
+        bucket = torch.empty((N * 11,), **o)
+        gsh = None
+        gpw = bucket[:3 * N].view(N, 3)
+        gs = bucket[3 * N:6 * N].view(N, 3)
+        gq = bucket[6 * N:10 * N].view(N, 4)
+        dal = bucket[10 * N:]
+    else:
+        bucket = torch.empty((N * (3 * k + 10),), **o)
+        gsh = bucket[:N * 3 * k].view(N, 3 * k)
+        gq = bucket[N * 3 * k:N * (3 * k + 4)].view(N, 4)
+        gpw = bucket[N * (3 * k + 4):N * (3 * k + 7)].view(N, 3)
+        gs = bucket[N * (3 * k + 7):].view(N, 3)
+        dal = torch.empty((N,), **o) if moments is not None else None
     dus = torch.empty((N, 2), **o) if moments is not None else None
-    dal = torch.empty((N,), **o) if moments is not None else None
     lib = _L()
     with torch.cuda.device(pws.device):
         _lib.check(lib.gsb_preprocess_backward(
@@ -431,3 +444,21 @@ def preprocessB(pws, rots, scales, shs, Rcw, tcw, twc, focal_x, focal_y, center_
             _ptr(gu), _ptr(gc), _ptr(gcol), _ptr(gpw), _ptr(gsh), _ptr(gs), _ptr(gq), _ptr(moments), _ptr(cinv2ds),
             _ptr(dus), _ptr(dal), _stream()), lib)
     return [gpw, gsh, gs, gq] + ([dus, dal] if moments is not None else [])
+
+
+def sh_grad_expand(pws, twcs, dloss_dcolors, sh_dim3, out=None):
+    """dloss_dshs[N, 3k] = sum over the V views of Y(dir_v) (x) dloss_dcolors[v]  (gsb_sh_grad_expand;
+    colour is linear in sh, kernel.cu:735-774).  pws[N,3], twcs[V,3] (camera centres),
+    dloss_dcolors[V,N,3]."""
+    pws = _chk(pws, "pws", last=3, ndim=2); twcs = _chk(twcs, "twcs", last=3, ndim=2)
+    g = _chk(dloss_dcolors, "dloss_dcolors", last=3, ndim=3)
+    _same_device(pws, twcs, g)
+    N, V, k = pws.shape[0], twcs.shape[0], int(sh_dim3)
+    if g.shape[0] != V or g.shape[1] != N or k not in (1, 4, 9, 16):
+        raise ValueError("sh_grad_expand: need twcs[V,3], dloss_dcolors[V,N,3], sh_dim3 in {1,4,9,16}")
+    if out is None:
+        out = torch.empty((N, 3 * k), dtype=torch.float32, device=pws.device)
+    lib = _L()
+    with torch.cuda.device(pws.device):
+        _lib.check(lib.gsb_sh_grad_expand(N, k, V, _ptr(pws), _ptr(twcs), _ptr(g), _ptr(out), _stream()), lib)
+    return out

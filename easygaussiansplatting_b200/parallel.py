@@ -232,6 +232,90 @@ class GradExchange:
             self._own = None
 
 
+class MultiViewStep:
+    """One data-parallel training step over the views of all ranks with the FACTORISED gradient sum.
+
+    Of the 236 B/Gaussian a view's parameter gradient occupies (SH degree 3), 192 B are dL/dsh =
+    Y(dir_v) (x) dL/dcolor_v: an outer product of a basis every rank can evaluate itself and 3
+    floats.  So the ranks exchange, per view, the 12-byte dL/dcolor (all-gather) and sum the
+    other 11 floats (all-reduce, 44 B), and every rank re-expands dL/dsh = sum_v Y(dir_v) (x)
+    dL/dcolor_v locally (gsb_sh_grad_expand): 44 + 12 V bytes per Gaussian instead of 236.
+
+        mv = MultiViewStep(pws, rots, scales, shs, alphas, group=None)
+        for cam, dl_fn in this rank's views of the step:          # 1 .. 8 / world views
+            image, ctx = mv.render(cam)
+            mv.backward(ctx, dloss_dimage)                        # accumulates locally
+        g = mv.reduce()   # ONE exchange: dict dpws dshs dalphas dscales drots, summed over every view
+                          # of every rank; g["dus"][i] is view i's own dL/du (densification statistic)
+
+    The collectives go through torch.distributed (NCCL on GPUs); the all-gather of the colours
+    is started before the expansion of the local result needs it and the all-reduce of the small
+    bucket overlaps that expansion.  world == 1 (or no process group) degenerates to local sums."""
+
+    def __init__(self, pws, rots, scales, shs, alphas, group=None):
+        self.pws, self.rots, self.scales, self.shs, self.alphas = pws, rots, scales, shs, alphas
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.k3 = shs.shape[1] // 3
+        self._small, self._colors, self._twcs, self._dus = None, [], [], []
+
+    def render(self, cam):
+        from . import ops
+        us, cinv2ds, colors, depths, areas, records = ops.preprocess(
+            self.pws, self.rots, self.scales, self.shs, cam.Rcw, cam.tcw, cam.twc, cam.fx, cam.fy, cam.cx, cam.cy,
+            cam.width, cam.height, alphas=self.alphas)
+        image, contrib, final_tau, ranges, gsid = ops.splat(cam.height, cam.width, us, cinv2ds, self.alphas, depths,
+                                                            colors, areas, records=records, capacity=True)
+        return image, (cam, us, cinv2ds, depths, colors, contrib, final_tau, ranges, gsid)
+
+    def backward(self, ctx, dloss_dimage):
+        from . import ops
+        cam, us, cinv2ds, depths, colors, contrib, final_tau, ranges, gsid = ctx
+        moments = ops.splatB(cam.height, cam.width, us, cinv2ds, self.alphas, depths, colors, contrib, final_tau,
+                             ranges, gsid, dloss_dimage, moments_only=True)
+        self._colors.append(moments[:, 6:9])          # dL/dcolor of this view
+        self._twcs.append(cam.twc.reshape(1, 3))
+        gpw, _, gs, gq, dus, dal = ops.preprocessB(
+            self.pws, self.rots, self.scales, self.shs, cam.Rcw, cam.tcw, cam.twc, cam.fx, cam.fy, cam.cx, cam.cy,
+            cam.width, cam.height, None, None, None, moments=moments, cinv2ds=cinv2ds, compact=True)
+        bucket = torch.as_strided(gpw, (gpw.shape[0] * 11,), (1,), gpw.storage_offset())  # [dpws|dscales|drots|dalphas]
+        self._small = bucket if self._small is None else self._small.add_(bucket)
+        self._dus.append(dus)
+
+    def reduce(self):
+        from . import ops
+        N = self.pws.shape[0]
+        colors = torch.stack(self._colors)                       # [V_local, N, 3] (contiguous copy)
+        twcs = torch.cat(self._twcs).contiguous()                # [V_local, 3]
+        small, dshs = factorised_sum(self._small, colors, twcs, self.group,
+                                     lambda tw, col: ops.sh_grad_expand(self.pws, tw, col, self.k3))
+        out = {"dpws": small[:3 * N].view(N, 3), "dscales": small[3 * N:6 * N].view(N, 3),
+               "drots": small[6 * N:10 * N].view(N, 4), "dalphas": small[10 * N:], "dshs": dshs, "dus": self._dus,
+               "bytes_per_rank": int(small.numel() * 4 + colors.numel() * 4)}
+        self._small, self._colors, self._twcs, self._dus = None, [], [], []
+        return out
+
+
+def factorised_sum(small, colors, twcs, group, expand):
+    """The collective part of MultiViewStep.reduce: `small` (flat 11 N bucket) is summed over the
+    ranks in place, `colors[V_local, N, 3]` / `twcs[V_local, 3]` are gathered from every rank (rank
+    order, then local view order) and `expand(all_twcs, all_colors)` -> dL/dsh runs while the
+    all-reduce is still in flight.  Works on any backend (gloo in the CPU tests)."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world == 1:
+        return small, expand(twcs, colors)
+    N = colors.shape[1]
+    all_colors = torch.empty((world * colors.shape[0], N, 3), dtype=colors.dtype, device=colors.device)
+    all_twcs = torch.empty((world * twcs.shape[0], 3), dtype=twcs.dtype, device=twcs.device)
+    w1 = dist.all_gather_into_tensor(all_twcs, twcs, group=group, async_op=True)
+    w2 = dist.all_gather_into_tensor(all_colors, colors, group=group, async_op=True)
+    w3 = dist.all_reduce(small, op=dist.ReduceOp.SUM, group=group, async_op=True)
+    w1.wait(); w2.wait()  # stream-ordered waits on NCCL; the all-reduce runs under the expansion
+    dshs = expand(all_twcs, all_colors)
+    w3.wait()
+    return small, dshs
+
+
 def prefer_fused_exchange(world):
     """Which gradient sum a training loop should use on `world` B200s of one NVSwitch node,
     from the measurements in profiles/ (bench.py times both at every world size):

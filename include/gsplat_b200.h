@@ -107,6 +107,16 @@ int gsb_preprocess_backward(int N, int sh_dim3, const float *pws, const float *r
                             const float *cinv2ds, float *dloss_dus_out, float *dloss_dalphas_out,
                             gsb_stream_t stream);
 
+/* dL/dsh from per-view dL/dcolor (extension; multi-view data parallelism).
+ * colour = 0.5 + sum_l Y_l(dir) sh_l is linear in sh and never clamped (kernel.cu:735-774), so
+ * dloss_dshs[n, l, c] = sum_v Y_l((pws[n] - twcs[v]) / |.|) * dloss_dcolors[v, n, c].
+ * gsb_preprocess_backward may then be called with dloss_dshs = NULL (it skips the 192-byte row),
+ * the V views of a step exchange 12 B per Gaussian and view instead of one 192-byte row, and every
+ * rank expands here.  twcs[V,3], dloss_dcolors[V,N,3] -> dloss_dshs[N,3*sh_dim3] (overwritten;
+ * views summed in index order; V = 1 reproduces gsb_preprocess_backward's row bit for bit). */
+int gsb_sh_grad_expand(int N, int sh_dim3, int V, const float *pws, const float *twcs, const float *dloss_dcolors,
+                       float *dloss_dshs, gsb_stream_t stream);
+
 /* ---- splat, phase 1: tile rectangles + patch count.
  * Replaces getRects + thrust::inclusive_scan + the D2H read of the total
  * (gausplat.cu:54-67, kernel.cu:82-122).  depths and areas are READ-WRITE (Gaussians that

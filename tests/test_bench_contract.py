@@ -19,7 +19,7 @@ def test_reference_arm_prints_one_json_line():
     assert d["value"] > 0 and d["ms_per_step"] > 0 and d["steps"] == 1 and d["n_gpus"] == 1
     assert d["config"]["gaussians"] == 1_000_000 and (d["config"]["width"], d["config"]["height"]) == (1920, 1080)
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "rows" in cb["sample"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "whole 1920x1080" in cb["sample"] and d["steps_timed"] == 1
     assert d["e2e"] == {"value": d["value"], "unit": "Mpixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["gpu_launches"] == 0 and d["vs_baseline"] is None
 

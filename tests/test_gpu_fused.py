@@ -267,3 +267,39 @@ def test_capacity_path_equals_exact_path(N, W, H):
     for a, b, c in zip(exact, small, narrow):
         assert torch.equal(a, b) and torch.equal(a, c)
     assert ops._CAPACITY[key][0] >= P  # relearnt
+
+
+@pytest.mark.parametrize("N,W,H,sh_dim,V", [(20000, 320, 240, 48, 3), (3000, 200, 120, 12, 1), (500, 64, 64, 3, 2)])
+def test_factorised_multi_view_step_matches_autograd_accumulation(N, W, H, sh_dim, V):
+    """parallel.MultiViewStep (per view: 11 small gradient floats accumulated + dL/dcolor kept; one
+    expansion dL/dsh = sum_v Y(dir_v) (x) dL/dcolor_v at the end) against the plain accumulation
+    of GSFunctionFused's gradients over the same V views.  V = 1: dL/dsh bit-identical."""
+    from easygaussiansplatting_b200.gsfunction import Camera, GSFunctionFused
+    from easygaussiansplatting_b200.parallel import MultiViewStep
+    from easygaussiansplatting_b200.scene import ring_camera
+    sc = scene(N, W, H, sh_dim, 4)
+    P = {k: t(sc[k]).requires_grad_() for k in ("pws", "shs", "scales", "rots")}
+    al = t(sc["alphas"][:, None]).requires_grad_()
+    us0 = torch.zeros((N, 2), device=DEV, requires_grad=True)
+    cams, dls = [], []
+    for v in range(V):
+        Rcw, tcw, twc = ring_camera(v, 8) if V > 1 else (sc["Rcw"], sc["tcw"], sc["twc"])
+        cams.append(Camera(W, H, sc["fx"], sc["fy"], sc["cx"], sc["cy"], t(Rcw), t(tcw), t(twc)))
+        dls.append(t(upstream_gradient(W, H, v) * (3.0 * W * H)))
+    for cam, dl in zip(cams, dls):
+        image, _ = GSFunctionFused.apply(P["pws"], P["shs"], al, P["scales"], P["rots"], us0, cam)
+        image.backward(dl)
+    mv = MultiViewStep(P["pws"].detach(), P["rots"].detach(), P["scales"].detach(), P["shs"].detach(), al.detach())
+    for cam, dl in zip(cams, dls):
+        img, ctx = mv.render(cam)
+        mv.backward(ctx, dl)
+    g = mv.reduce()
+    assert g["bytes_per_rank"] == 4 * N * (11 + 3 * V)
+    for name, want in (("dpws", P["pws"].grad), ("dshs", P["shs"].grad), ("dscales", P["scales"].grad),
+                       ("drots", P["rots"].grad), ("dalphas", al.grad.reshape(-1))):
+        got = g[name].reshape(want.shape)
+        if V == 1:
+            assert torch.equal(got, want), name
+        else:
+            err = float((got - want).abs().max() / want.abs().max().clamp_min(1e-30))
+            assert err <= 2e-6, (name, err)

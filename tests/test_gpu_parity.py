@@ -392,3 +392,20 @@ def test_config2_full_size_properties_and_oracle():
     assert torch.equal(again[0], image) and torch.equal(again[1], contrib) and torch.equal(again[4], gsid)
     # transmittance bound: 0 <= tau <= 1 and image finite
     assert torch.isfinite(image).all() and ftau.min() >= 0 and ftau.max() <= 1
+
+
+def test_reference_backward_gpu_script_unmodified():
+    """The reference's own parity script backward_gpu.py (81-152: 19 `[OK]` checks against
+    backward_cpu.py at abs 1e-4) and forward_gpu.py (47-60), run UNMODIFIED on this gsplatcu.
+    Needs the copies baseline/build_ref_gpu.sh puts under baseline/_ref/py (they travel with the
+    gpurun snapshot; absent on a box that never saw the reference tree -> skipped)."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "benchmarks"))
+    import run_reference_scripts as rrs
+    if not rrs.available():
+        pytest.skip("baseline/_ref/py not installed")
+    res = rrs.run("ours")
+    b = res["backward_gpu"]
+    assert b["ng"] == 0 and b["ok"] == 19, b["lines"]
+    f = res["forward_gpu"]
+    assert f["image_shape"] == [3, 546, 979] and f["image_max"] > 0.1

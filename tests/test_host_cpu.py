@@ -107,3 +107,48 @@ def test_multiview_grad_allreduce_gloo_world2(tmp_path):
     outs = [p.communicate(timeout=120)[0] for p in procs]
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0 and ("ok %d" % r) in o, o
+
+
+_WORKER_FACT = r"""
+import os, sys, numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, %r)
+from easygaussiansplatting_b200.parallel import factorised_sum
+from oracle import oracle as orc
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", rank=rank, world_size=world)
+N, K3, VL = 300, 16, 2                       # 2 local views per rank -> 4 views in total
+rng = np.random.default_rng(7)               # same on every rank: positions, every view's data
+pws = rng.normal(size=(N, 3)).astype(np.float32) * 3
+twc_all = rng.normal(size=(world * VL, 3)).astype(np.float32) * 8
+col_all = rng.normal(size=(world * VL, N, 3)).astype(np.float32)
+small_all = rng.normal(size=(world, 11 * N)).astype(np.float32)
+def basis(twc):                              # Y_l(dir) of every Gaussian for one camera centre: the oracle's dcolor/dsh
+    return orc.sh2color(np.zeros((N, 3 * K3), np.float32), pws, twc)[1].reshape(N, K3)
+def expand(tw, col):                         # CPU stand-in of ops.sh_grad_expand (same contract)
+    out = np.zeros((N, K3, 3))
+    for v in range(tw.shape[0]):
+        out += basis(tw[v].numpy())[:, :, None] * col[v].numpy().astype(np.float64)[:, None, :]
+    return torch.from_numpy(out.reshape(N, 3 * K3))
+lo = rank * VL
+small, dshs = factorised_sum(torch.from_numpy(small_all[rank].copy()), torch.from_numpy(col_all[lo:lo + VL].copy()),
+                             torch.from_numpy(twc_all[lo:lo + VL].copy()), None, expand)
+assert np.allclose(small.numpy(), small_all.sum(0), atol=1e-5)
+want = expand(torch.from_numpy(twc_all), torch.from_numpy(col_all))    # every view, in rank order
+assert torch.allclose(dshs, want, atol=1e-9), float((dshs - want).abs().max())
+dist.barrier(); dist.destroy_process_group()
+print("ok", rank)
+"""
+
+
+def test_factorised_multiview_sum_gloo_world2(tmp_path):
+    """parallel.factorised_sum on 2 CPU ranks x 2 local views: the 11-float bucket is all-reduced,
+    the per-view dL/dcolor and camera centres are gathered in rank order and the expansion
+    sum_v Y(dir_v) (x) dL/dcolor_v sees all 4 views on every rank."""
+    script = tmp_path / "wf.py"
+    script.write_text(_WORKER_FACT % ROOT)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29533", WORLD_SIZE="2")
+    procs = [subprocess.Popen([sys.executable, str(script)], env=dict(env, RANK=str(r)),
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=120)[0] for p in procs]
+    for r, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0 and ("ok %d" % r) in o, o
