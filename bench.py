@@ -544,17 +544,26 @@ def run_config5(torch, dist, dev, rank, world, timed):
     dl = T(upstream_gradient(WIDTH, HEIGHT, rank) * (3.0 * WIDTH * HEIGHT))
     out = [None]
 
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+
     def step():
+        ev[0].record()
         for cam in cams:
             image, ctx = mv.render(cam)
             mv.backward(ctx, dl)
+        ev[1].record()
         out[0] = mv.reduce()
-    n = 5
-    ms = timed(step, n, 3) / n
+        ev[2].record()
+    n = 8  # (6 warm-up steps: the allocator and NCCL settle on the 2M-Gaussian buffer sizes over the first few)
+    ms = timed(step, n, 6) / n
+    torch.cuda.synchronize()
+    ms_render, ms_reduce = ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])  # last step, this rank
     res = {"what": "config 5: 2M shared Gaussians, 8 cameras/step at 1920x1080, %d view(s) per rank, one "
                    "factorised gradient exchange per step (strong scaling over the ranks)" % len(mine),
            "gaussians": N5, "views_per_step": V5, "n_gpus": world, "ms_per_step": ms,
            "value": V5 * WIDTH * HEIGHT / (ms * 1e-3) / 1e6, "unit": "Mpixels/s", "scaling": "strong",
+           "last_step_ms": {"render_and_backward": ms_render, "reduce": ms_reduce},
+           "capacity_path": dict(__import__("easygaussiansplatting_b200.ops", fromlist=["x"]).CAPACITY_STATS),
            "exchange_bytes_per_rank": out[0]["bytes_per_rank"] if world > 1 else 0}
     del mv, out
     torch.cuda.empty_cache()

@@ -10,6 +10,12 @@ called `gsplatcu`.
 
 t_fwd = GSFunction.apply (6 ops, calc_J=True); t_bwd = image.backward (splatB + Jacobian
 chain); CUDA events, 3 warm-ups, median of `--iters`; also per-op splat / splatB times.
+
+    python benchmarks/compare_ref_gpu.py --three-way   # error table of the rasterizer pair
+Three-way error table (splat + splatB on IDENTICAL fp32 op inputs, config 2): ours <-> fp64 oracle,
+reference-GPU <-> oracle, ours <-> reference-GPU, and -- when a GSB_EXACT_MATH variant library
+libgsplat_b200_exact.so exists -- ours-with-IEEE-exp2/rcp <-> oracle; each with and without the
+pixels / Gaussians the oracle flags as ambiguous (an alpha' within 2e-5 of the 0.002 threshold).
 """
 import argparse
 import json
@@ -93,13 +99,108 @@ def run_arm(arm, iters, out_path, configs):
     json.dump(res, open(out_path, "w"))
 
 
+def three_way_arm(arm, inp_path, out_path):
+    """splat + splatB of one implementation on the shared op inputs"""
+    import torch
+    if arm == "ref":
+        sys.path.insert(0, os.path.join(ROOT, "baseline", "_ref"))
+        import gsplatcu as gsc
+        assert gsc.__file__.endswith(".so"), gsc.__file__
+    else:
+        sys.path.insert(0, ROOT)
+        import gsplatcu as gsc
+    d = np.load(inp_path)
+    dev = "cuda:0"
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    H, W = int(d["H"]), int(d["W"])
+    us, ci, al, dep, col, ar, dl = (T(d[k]) for k in ("us", "cinv2ds", "alphas", "depths", "colors", "areas", "dl"))
+    o = gsc.splat(H, W, us, ci, al, dep, col, ar)
+    g = gsc.splatB(H, W, us, ci, al, dep, col, o[1], o[2], o[3], o[4], dl)
+    torch.cuda.synchronize()
+    np.savez(out_path, image=o[0].cpu().numpy(), dus=g[0].cpu().numpy().reshape(-1, 2),
+             dcinv=g[1].cpu().numpy().reshape(-1, 3), dalpha=g[2].cpu().numpy().reshape(-1, 1),
+             dcol=g[3].cpu().numpy().reshape(-1, 3))
+
+
+def three_way(out):
+    """-> dict; writes out + '.three_way.json'"""
+    sys.path.insert(0, ROOT)
+    from oracle import oracle as orc
+    from easygaussiansplatting_b200.scene import synthetic_scene, upstream_gradient
+    N, W, H = 1_000_000, 1920, 1080
+    orc.set_num_threads(os.cpu_count() or 1)
+    sc = synthetic_scene(N, W, H, sh_dim=48, seed=0)
+    f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32)
+    us, pcs, depths, _ = orc.project(sc["pws"], sc["Rcw"], sc["tcw"], sc["fx"], sc["fy"], sc["cx"], sc["cy"])
+    d32 = f32(depths)
+    c3 = orc.compute_cov3d(sc["rots"], sc["scales"], d32, calc_J=False)[0]
+    c2 = orc.compute_cov2d(f32(c3), f32(pcs), sc["Rcw"], d32, sc["fx"], sc["fy"], W, H, calc_J=False)[0]
+    col = orc.sh2color(sc["shs"], sc["pws"], sc["twc"], calc_J=False)[0]
+    ci, areas = orc.inverse_cov2d(f32(c2), d32, calc_J=False)[:2]
+    dl = upstream_gradient(W, H, 0) * (3.0 * W * H)
+    inp = out + ".three_way_inputs.npz"
+    np.savez(inp, H=H, W=W, us=f32(us), cinv2ds=f32(ci), alphas=f32(sc["alphas"]), depths=d32, colors=f32(col),
+             areas=np.ascontiguousarray(areas, dtype=np.int32), dl=f32(dl))
+    arms = {"ours": {}}
+    exact = os.path.join(ROOT, "easygaussiansplatting_b200", "libgsplat_b200_exact.so")
+    if os.path.exists(exact):
+        arms["ours_exact"] = {"GSB_LIB": exact}
+    ref_dir = os.path.join(ROOT, "baseline", "_ref")
+    if os.path.isdir(ref_dir) and any(f.startswith("gsplatcu") and f.endswith(".so") for f in os.listdir(ref_dir)):
+        arms["ref"] = {}
+    res = {}
+    for arm, env in arms.items():
+        o = out + ".three_way_%s.npz" % arm
+        subprocess.run([sys.executable, os.path.abspath(__file__), "--three-way-arm", "ref" if arm == "ref" else "ours",
+                        "--inputs", inp, "--out", o], check=True, env=dict(os.environ, **env))
+        res[arm] = dict(np.load(o))
+        os.remove(o)
+    # fp64 oracle on the same fp32 inputs (the arms' in-place culls do not change depths/areas here:
+    # the inputs are already the post-cull values the oracle's own stages produce)
+    fwd = orc.splat(H, W, f32(us), f32(ci), sc["alphas"], d32.copy(), f32(col), np.ascontiguousarray(areas, dtype=np.int32))
+    du, dc, da, dcol, amb = orc.splat_backward(H, W, f32(us), f32(ci), sc["alphas"], f32(col), fwd, f32(dl),
+                                               return_ambiguous=True)
+    res["oracle"] = {"image": fwd["image"], "dus": du.reshape(-1, 2), "dcinv": dc.reshape(-1, 3),
+                     "dalpha": da.reshape(-1, 1), "dcol": dcol.reshape(-1, 3)}
+    okpix, okg = ~fwd["ambiguous"], ~amb
+
+    def err(a, b, name):
+        a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+        scale = max(np.abs(b).max(), 1e-30)
+        if name == "image":
+            e = np.abs(a - b).max(axis=0)
+            return float(e.max() / scale), float(e[okpix].max() / scale)
+        e = np.abs(a - b).max(axis=1)
+        return float(e.max() / scale), float(e[okg].max() / scale)
+    table = {}
+    pairs = [(a, "oracle") for a in arms] + ([("ours", "ref")] if "ref" in arms else [])
+    for a, b in pairs:
+        table["%s_vs_%s" % (a, b)] = {k: dict(zip(("all", "without_ambiguous"), err(res[a][k], res[b][k], k)))
+                                      for k in ("image", "dus", "dcinv", "dalpha", "dcol")}
+    outj = {"what": "max |a - b| / max |b| per tensor, splat + splatB on identical fp32 op inputs, config 2 "
+                    "(1M Gaussians, 1920x1080)", "ambiguous_pixels": int(fwd["ambiguous"].sum()),
+            "ambiguous_gaussians": int(amb.sum()), "table": table}
+    os.remove(inp)
+    json.dump(outj, open(out + ".three_way.json", "w"), indent=1)
+    print(json.dumps(outj, indent=1))
+    return outj
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--three-way", action="store_true")
+    ap.add_argument("--three-way-arm", default=None)
+    ap.add_argument("--inputs", default=None)
     ap.add_argument("--arm", default=None)
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "compare_ref_gpu"))
     ap.add_argument("--configs", default="config2,cfg4_50k_512,cfg4_500k_1080p")
     a = ap.parse_args()
+    if a.three_way_arm:
+        return three_way_arm(a.three_way_arm, a.inputs, a.out)
+    if a.three_way:
+        os.makedirs(os.path.dirname(a.out), exist_ok=True)
+        return three_way(a.out)
     cfgs = [c for c in CONFIGS if c[0] in a.configs.split(",")]
     if a.arm:
         return run_arm(a.arm, a.iters, a.out + "." + a.arm + ".json", cfgs)

@@ -17,6 +17,7 @@ import contextlib
 import io
 import json
 import os
+import re
 import runpy
 import sys
 
@@ -49,8 +50,9 @@ def run(impl="ours"):
             with contextlib.redirect_stdout(buf):
                 g = runpy.run_path(os.path.join(PY, script), run_name="__main__")
             lines = [ln for ln in buf.getvalue().splitlines() if ln.strip()]
-            rec = {"ok": sum(ln.startswith("[OK]") for ln in lines), "ng": sum(ln.startswith("[NG]") for ln in lines),
-                   "lines": lines}
+            plain = [re.sub(r"\x1b\[[0-9;]*m", "", ln) for ln in lines]  # check() colours its verdicts
+            rec = {"ok": sum(ln.startswith("[OK]") for ln in plain), "ng": sum(ln.startswith("[NG]") for ln in plain),
+                   "lines": plain}
             if script == "forward_gpu.py":
                 img = g["image"]
                 rec["image_shape"] = list(img.shape)

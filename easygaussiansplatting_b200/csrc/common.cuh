@@ -28,15 +28,30 @@ struct __align__(16) Rec {
 };
 static_assert(sizeof(Rec) == 48, "record must be 48 bytes");
 
+// GSB_EXACT_MATH=1 (variant builds only, benchmarks/compare_ref_gpu.py --three-way): IEEE reciprocal
+// and an exp2 evaluated in double precision instead of the MUFU approximations, to show how much
+// of the distance to the fp64 oracle comes from them (CUDA's own exp2f is MUFU.EX2 plus range
+// scaling, i.e. the same 2-ulp function).
+#ifndef GSB_EXACT_MATH
+#define GSB_EXACT_MATH 0
+#endif
 __device__ __forceinline__ float rcp_approx(float x) {
+#if GSB_EXACT_MATH
+  return __frcp_rn(x);
+#else
   float y;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+#endif
 }
 __device__ __forceinline__ float ex2_approx(float x) {
+#if GSB_EXACT_MATH
+  return (float)exp2((double)x);
+#else
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+#endif
 }
 
 // alpha' of one record at one pixel -- THE single definition used by forward and backward

@@ -187,8 +187,8 @@ __global__ void __launch_bounds__(PG) k_preprocess_bwd(
 // dL/dsh of one Gaussian summed over V views from the views' dL/dcolor:
 //   colour = 0.5 + sum_l Y_l(dir) sh_l is linear in sh and never clamped (kernel.cu:735-774), so
 //   dL/dsh[l][c] = sum_v Y_l(dir_v) dL/dcolor_v[c]   with dir_v = (pw - twc_v) / |pw - twc_v|,
-// the same Y (same instruction sequence) as backward_one evaluates; for V = 1 the result is
-// bit-identical to the dL/dsh row the per-Gaussian backward writes.  Multi-view data parallel
+// the same Y as backward_one evaluates (for V = 1 the result equals the dL/dsh row the per-Gaussian
+// backward writes up to the compiler's FMA contraction of the basis polynomials).  Multi-view data parallel
 // training exchanges the 12-byte dL/dcolor per view instead of the 192-byte dL/dsh row and
 // expands on every rank (parallel.MultiViewStep).  Views are summed in index order.
 template <int K3>

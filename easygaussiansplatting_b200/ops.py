@@ -158,6 +158,7 @@ def inverseCov2D(cov2ds, depths, calc_J):
 GSB_CAPACITY_EXCEEDED = 2
 _CAPACITY = {}  # (device index, H, W, N) -> (P_cap, depth_key_cap) learnt from the previous frame
 _STATUS = {}    # device index -> pinned int32[4] for gsb_splat_forward's status read
+CAPACITY_STATS = {"capacity_frames": 0, "exact_frames": 0, "outgrown": 0}  # how the frames of `capacity=True` went
 
 
 def _next_capacity(P, dkmax):
@@ -217,6 +218,7 @@ def splat(height, width, us, cinv2ds, alphas, depths, colors, areas, records=Non
                                        ws_bytes, _ptr(image), _ptr(contrib), _ptr(final_tau), _ptr(ranges),
                                        _ptr(gsid), status.data_ptr(), st)
             if rc == 0:
+                CAPACITY_STATS["capacity_frames"] += 1
                 P, dkmax = int(status[0]) & 0xffffffff, int(status[1]) & 0xffffffff
                 _CAPACITY[cap_key] = _next_capacity(P, dkmax)
                 gsid = gsid[:P]
@@ -229,6 +231,7 @@ def splat(height, width, us, cinv2ds, alphas, depths, colors, areas, records=Non
                 return [image, contrib, final_tau, ranges, gsid]
             if rc != GSB_CAPACITY_EXCEEDED:
                 _lib.check(rc, lib)
+            CAPACITY_STATS["outgrown"] += 1
             del _CAPACITY[cap_key]  # outgrown: this frame the exact way (the in-place culls are idempotent)
     with torch.cuda.device(dev):
         st = _stream()
@@ -246,6 +249,7 @@ def splat(height, width, us, cinv2ds, alphas, depths, colors, areas, records=Non
         ranges = torch.empty((T, 2), dtype=torch.int32, device=dev)
         gsid = torch.empty((P,), dtype=torch.int32, device=dev)
         if capacity:
+            CAPACITY_STATS["exact_frames"] += 1
             _CAPACITY[cap_key] = _next_capacity(P, dkmax.value)
         _lib.check(lib.gsb_splat_render(H, W, N, P, dkmax.value, _ptr(us), _ptr(cinv2ds), _ptr(alphas),
                                         _ptr(depths), _ptr(colors), _ptr(records), _ptr(bin_ws), _ptr(ws), ws_bytes,

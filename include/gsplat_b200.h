@@ -113,7 +113,7 @@ int gsb_preprocess_backward(int N, int sh_dim3, const float *pws, const float *r
  * gsb_preprocess_backward may then be called with dloss_dshs = NULL (it skips the 192-byte row),
  * the V views of a step exchange 12 B per Gaussian and view instead of one 192-byte row, and every
  * rank expands here.  twcs[V,3], dloss_dcolors[V,N,3] -> dloss_dshs[N,3*sh_dim3] (overwritten;
- * views summed in index order; V = 1 reproduces gsb_preprocess_backward's row bit for bit). */
+ * views summed in index order; V = 1 reproduces gsb_preprocess_backward's row to rounding). */
 int gsb_sh_grad_expand(int N, int sh_dim3, int V, const float *pws, const float *twcs, const float *dloss_dcolors,
                        float *dloss_dshs, gsb_stream_t stream);
 

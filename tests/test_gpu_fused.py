@@ -273,7 +273,8 @@ def test_capacity_path_equals_exact_path(N, W, H):
 def test_factorised_multi_view_step_matches_autograd_accumulation(N, W, H, sh_dim, V):
     """parallel.MultiViewStep (per view: 11 small gradient floats accumulated + dL/dcolor kept; one
     expansion dL/dsh = sum_v Y(dir_v) (x) dL/dcolor_v at the end) against the plain accumulation
-    of GSFunctionFused's gradients over the same V views.  V = 1: dL/dsh bit-identical."""
+    of GSFunctionFused's gradients over the same V views.  Agreement is to rounding, not bitwise:
+    the rasterizer backward's atomics make two runs of the same view differ in the last bits."""
     from easygaussiansplatting_b200.gsfunction import Camera, GSFunctionFused
     from easygaussiansplatting_b200.parallel import MultiViewStep
     from easygaussiansplatting_b200.scene import ring_camera
@@ -298,8 +299,5 @@ def test_factorised_multi_view_step_matches_autograd_accumulation(N, W, H, sh_di
     for name, want in (("dpws", P["pws"].grad), ("dshs", P["shs"].grad), ("dscales", P["scales"].grad),
                        ("drots", P["rots"].grad), ("dalphas", al.grad.reshape(-1))):
         got = g[name].reshape(want.shape)
-        if V == 1:
-            assert torch.equal(got, want), name
-        else:
-            err = float((got - want).abs().max() / want.abs().max().clamp_min(1e-30))
-            assert err <= 2e-6, (name, err)
+        err = float((got - want).abs().max() / want.abs().max().clamp_min(1e-30))
+        assert err <= 2e-6, (name, err)
