@@ -267,10 +267,10 @@ int gsb_splat_render(int H, int W, int N, int64_t P, uint32_t depth_key_max, con
               "splat: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
   SortLayout SL{};
-  if (P > 0) {
+  {
     int rc = sort_layout(N, H, W, P, &SL);
     if (rc) return rc;
-    GSB_REQUIRE(ws_bytes >= SL.bytes, "splat: workspace too small");
+    GSB_REQUIRE(ws != nullptr && ws_bytes >= SL.bytes, "splat: workspace too small");
   }
   const BinLayout BL = bin_layout(N);
   GSB_REQUIRE((reinterpret_cast<uintptr_t>(packed_records) & 15) == 0, "splat: packed_records misaligned");
@@ -280,11 +280,7 @@ int gsb_splat_render(int H, int W, int N, int64_t P, uint32_t depth_key_max, con
   const Rec *recs = P > 0 ? reinterpret_cast<const Rec *>(static_cast<char *>(ws) + SL.recs) : nullptr;
   if (P > 0 && packed_records != nullptr) recs = static_cast<const Rec *>(packed_records);
   // with P == 0 the workspace may be a dummy: every tile is empty, any variant just writes zeros
-  int *tile_counter = P > 0 ? reinterpret_cast<int *>(static_cast<char *>(ws) + SL.counters) : nullptr;
-  if (tile_counter == nullptr) {
-    GSB_REQUIRE(ws != nullptr && ws_bytes >= sizeof(int), "splat: workspace too small");
-    tile_counter = static_cast<int *>(ws);
-  }
+  int *tile_counter = reinterpret_cast<int *>(static_cast<char *>(ws) + SL.counters);
   // sparse frame (< 48 patches per tile on average): persistent grid + tile queue
   const int64_t T = (int64_t)((W + GSB_TILE - 1) / GSB_TILE) * ((H + GSB_TILE - 1) / GSB_TILE);
   int *const work_counter = tile_counter;
@@ -320,8 +316,8 @@ int gsb_splat_forward(int H, int W, int N, const float *us, const float *cinv2ds
   if (N == 0) {  // nothing to bin: every tile is empty
     GSB_CUDA_TRY(cudaMemsetAsync(patch_range_per_tile, 0,
                                  sizeof(int32_t) * 2 * (size_t)((W + GSB_TILE - 1) / GSB_TILE) * ((H + GSB_TILE - 1) / GSB_TILE), st));
-    return launch_draw(H, W, patch_range_per_tile, nullptr, gsid_per_patch, image, contrib, final_tau,
-                       static_cast<int *>(ws), static_cast<int *>(ws), st);
+    int *work = reinterpret_cast<int *>(static_cast<char *>(ws) + SL.counters);
+    return launch_draw(H, W, patch_range_per_tile, nullptr, gsid_per_patch, image, contrib, final_tau, work, work, st);
   }
   rc = launch_sort_and_pack(H, W, N, P_cap, depth_key_cap, us, cinv2ds, alphas, depths, colors, bin_ws, BL, ws, SL,
                             patch_range_per_tile, gsid_per_patch, packed_records == nullptr, &sr, st);
@@ -348,10 +344,11 @@ int gsb_splat_forward(int H, int W, int N, const float *us, const float *cinv2ds
 }
 
 size_t gsb_splat_backward_workspace_bytes(int N, int H, int W, int64_t P) {
-  (void)H; (void)W;
   // per-Gaussian records (256-B aligned; only when they have to be rebuilt, P > 0) + the [N,9]
   // moment accumulators
-  return (size_t)(P > 0 && N > 0 ? N : 1) * sizeof(Rec) + 512 + (size_t)(N > 0 ? N : 1) * 9 * sizeof(float) + 512;
+  const size_t T = (size_t)((W + GSB_TILE - 1) / GSB_TILE) * (size_t)((H + GSB_TILE - 1) / GSB_TILE);
+  return (size_t)(P > 0 && N > 0 ? N : 1) * sizeof(Rec) + 512 + (size_t)(N > 0 ? N : 1) * 9 * sizeof(float) + 512 +
+         (T + 2) * sizeof(int);  // + the rasterizer's work area
 }
 
 int gsb_splat_backward(int H, int W, int N, int64_t P, const float *us, const float *cinv2ds,

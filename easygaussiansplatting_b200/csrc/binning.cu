@@ -514,8 +514,8 @@ int launch_bin(int H, int W, int N, const float *us, float *depths, int32_t *are
 
 // ---------------------------------------------------------------- phase 2 host side
 int sort_layout(int N, int H, int W, int64_t P, SortLayout *out) {
-  (void)H; (void)W;
   SortLayout L{};
+  const size_t T = (size_t)((W + TILE - 1) / TILE) * (size_t)((H + TILE - 1) / TILE);
   const size_t n = (size_t)(P > 0 ? P : 1);
   const size_t ng = (size_t)(N > 0 ? N : 1);
   const size_t tiles = (n + RX_TILE - 1) / RX_TILE;
@@ -525,7 +525,7 @@ int sort_layout(int N, int H, int W, int64_t P, SortLayout *out) {
   L.vals_a = o; o = align_up(o + n * sizeof(int32_t), 256);
   L.vals_b = o; o = align_up(o + n * sizeof(int32_t), 256);
   L.recs = o;   o = align_up(o + ng * sizeof(Rec), 256);  // one record per Gaussian
-  L.counters = o; o = align_up(o + 64, 256);  // persistent-kernel tile counter
+  L.counters = o; o = align_up(o + (T + 2) * sizeof(int), 256);  // rasterizer work area (launch_tile_list)
   // zeroed per call: [status | global digit histograms | per-tile digit counts of every pass]
   L.sort_state = o;
   L.hist = o + 64;

@@ -163,7 +163,7 @@ __device__ __forceinline__ void sts64u(uint32_t a, uint32_t x, uint32_t y) {
 __global__ void __launch_bounds__(128, BWD4_MINBLOCKS) k_draw_bwd4(
     int W, int H, int gx, int T, const int2 *__restrict__ ranges, const Rec *__restrict__ recs,
     const int32_t *__restrict__ gsid, const int32_t *__restrict__ contrib, const float *__restrict__ final_tau,
-    const float *__restrict__ dloss_dgammas, float *__restrict__ moments, int *__restrict__ work_counter) {
+    const float *__restrict__ dloss_dgammas, float *__restrict__ moments, int *__restrict__ work) {
   __shared__ __align__(16) unsigned char s_ring[4][B4_RING * B4_CHUNK_BYTES];  // gathered records, per warp
   __shared__ __align__(16) unsigned char s_w[4][B4_W_BYTES];                   // weight rows, per warp
   __shared__ __align__(16) float s_dl[4][3][64];                               // dL/dgamma of the block
@@ -179,14 +179,16 @@ __global__ void __launch_bounds__(128, BWD4_MINBLOCKS) k_draw_bwd4(
   const uint32_t dummy_addr = smem_u32(&s_dummy);
   if (threadIdx.x < 12) reinterpret_cast<float *>(&s_dummy)[threadIdx.x] = 0.0f;
   __syncthreads();  // (the only CTA-wide barrier: start-up)
-  const int items = 4 * T;
+  (void)T;
+  const int items = 4 * work[1];  // 8x8 blocks of the tiles that have patches (k_tile_list, raster_fwd3.cu)
+  const int *__restrict__ tile_list = work + 2;
 
   for (;;) {
     int item = 0;
-    if (lane == 0) item = atomicAdd(work_counter, 1);
+    if (lane == 0) item = atomicAdd(work, 1);
     item = __shfl_sync(0xffffffffu, item, 0);
     if (item >= items) break;
-    const int tile = item >> 2, blk = item & 3;
+    const int tile = __ldg(tile_list + (item >> 2)), blk = item & 3;
     const int2 range = __ldg(ranges + tile);
     const int len = range.y - range.x;
     if (len <= 0) continue;
@@ -329,8 +331,9 @@ int launch_draw_bwd4_kernel(int H, int W, const int32_t *ranges, const Rec *recs
                             float *moments, int *work_counter, cudaStream_t st) {
   const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
   const int T = gx * gy;
-  if (work_counter == nullptr) return set_arg_error("drawB: work counter missing");
-  GSB_CUDA_TRY(cudaMemsetAsync(work_counter, 0, sizeof(int), st));
+  if (work_counter == nullptr) return set_arg_error("drawB: work area missing");
+  int rc = launch_tile_list(H, W, ranges, nullptr, nullptr, nullptr, work_counter, st);  // tiles with patches
+  if (rc) return rc;
   int dev = 0, sms = 148;
   GSB_CUDA_TRY(cudaGetDevice(&dev));
   GSB_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));

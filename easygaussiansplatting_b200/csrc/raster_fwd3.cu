@@ -65,6 +65,58 @@ __device__ __forceinline__ float2 f3_alpha(const float4 &q0, const float4 &q1, c
 }
 }  // namespace
 
+// Work list of the two rasterizers: the tiles that have patches, compacted (work[1] = how many,
+// work[2..] = their ids; work[0] is the kernels' item counter).  A tile without patches keeps
+// image 0, contrib 0, tau 0 (kernel.cu:182-183): when outputs are given this pass writes those
+// zeros itself with 16-byte stores -- one warp per tile -- so the sparse corner of BASELINE config 4
+// (50k Gaussians at 4K: 32 400 tiles, most of them empty) costs one streaming pass over the
+// frame instead of one queue item per 8x8 block.
+__global__ void __launch_bounds__(256) k_tile_list(int W, int H, int gx, int T, const int2 *__restrict__ ranges,
+                                                   float *__restrict__ image, int32_t *__restrict__ contrib,
+                                                   float *__restrict__ final_tau, int *__restrict__ work) {
+  const int lane = threadIdx.x & 31;
+  const int tile = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (tile >= T) return;
+  const int2 r = __ldg(ranges + tile);
+  if (r.y - r.x > 0) {
+    if (lane == 0) work[2 + atomicAdd(work + 1, 1)] = tile;
+    return;
+  }
+  if (image == nullptr) return;
+  const size_t HW = (size_t)H * W;
+  const int x0 = (tile % gx) * TILE + (lane & 1) * 8, y = (tile / gx) * TILE + (lane >> 1);
+  if (y >= H || x0 >= W) return;
+  const size_t pix = (size_t)y * W + x0;
+  if ((W & 3) == 0 && x0 + 8 <= W) {  // 8 pixels = two 16-byte stores per plane
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      *reinterpret_cast<float4 *>(image + pix + 4 * h) = z;
+      *reinterpret_cast<float4 *>(image + HW + pix + 4 * h) = z;
+      *reinterpret_cast<float4 *>(image + 2 * HW + pix + 4 * h) = z;
+      *reinterpret_cast<int4 *>(contrib + pix + 4 * h) = make_int4(0, 0, 0, 0);
+      *reinterpret_cast<float4 *>(final_tau + pix + 4 * h) = z;
+    }
+  } else {
+    for (int x = x0; x < min(x0 + 8, W); x++) {
+      const size_t q = (size_t)y * W + x;
+      image[q] = 0.f; image[HW + q] = 0.f; image[2 * HW + q] = 0.f;
+      contrib[q] = 0; final_tau[q] = 0.f;
+    }
+  }
+}
+
+int launch_tile_list(int H, int W, const int32_t *ranges, float *image, int32_t *contrib, float *final_tau,
+                     int *work, cudaStream_t st) {
+  const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
+  const int T = gx * gy;
+  GSB_CUDA_TRY(cudaMemsetAsync(work, 0, 2 * sizeof(int), st));
+  k_tile_list<<<(T + 7) / 8, 256, 0, st>>>(W, H, gx, T, reinterpret_cast<const int2 *>(ranges), image, contrib,
+                                           final_tau, work);
+  GSB_CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
 __global__ void __launch_bounds__(128, FWD3_MINBLOCKS) k_draw3(int W, int H, int gx, int T,
                                                                const int2 *__restrict__ ranges,
                                                                const Rec *__restrict__ recs,
@@ -72,7 +124,7 @@ __global__ void __launch_bounds__(128, FWD3_MINBLOCKS) k_draw3(int W, int H, int
                                                                float *__restrict__ image,
                                                                int32_t *__restrict__ contrib,
                                                                float *__restrict__ final_tau,
-                                                               int *__restrict__ work_counter) {
+                                                               int *__restrict__ work) {
   __shared__ __align__(16) unsigned char s_ring[4][F3_RING * F3_CHUNK_BYTES];  // gathered records, per warp
   __shared__ __align__(16) uint2 s_list[4][34];  // (record address, patch index + 1) of a chunk's survivors
   __shared__ __align__(16) Rec s_dummy;          // all-zero record (alpha = 0): pads an odd survivor count
@@ -85,14 +137,16 @@ __global__ void __launch_bounds__(128, FWD3_MINBLOCKS) k_draw3(int W, int H, int
   const uint32_t dummy_addr = smem_u32(&s_dummy);
   if (threadIdx.x < 12) reinterpret_cast<float *>(&s_dummy)[threadIdx.x] = 0.0f;
   __syncthreads();  // (the only CTA-wide barrier: start-up)
-  const int items = 4 * T;
+  (void)T;
+  const int items = 4 * work[1];  // 8x8 blocks of the tiles that have patches (k_tile_list)
+  const int *__restrict__ tile_list = work + 2;
 
   for (;;) {
     int item = 0;
-    if (lane == 0) item = atomicAdd(work_counter, 1);
+    if (lane == 0) item = atomicAdd(work, 1);
     item = __shfl_sync(0xffffffffu, item, 0);
     if (item >= items) break;
-    const int tile = item >> 2, blk = item & 3;
+    const int tile = __ldg(tile_list + (item >> 2)), blk = item & 3;
     const int tx = tile % gx, ty = tile / gx;
     const int rx0 = tx * TILE + (blk & 1) * 8, ry0 = ty * TILE + (blk >> 1) * 8;
     if (rx0 >= W || ry0 >= H) continue;  // block entirely outside the image
@@ -206,8 +260,10 @@ int launch_draw3(int H, int W, const int32_t *ranges, const Rec *recs, const int
   const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
   if (gx <= 0 || gy <= 0) return 0;
   const int T = gx * gy;
-  if (work_counter == nullptr) return set_arg_error("draw: work counter missing");
-  GSB_CUDA_TRY(cudaMemsetAsync(work_counter, 0, sizeof(int), st));
+  if (work_counter == nullptr) return set_arg_error("draw: work area missing");
+  // work list (and the zeros of the empty tiles) first; it also clears the item counter
+  int rc = launch_tile_list(H, W, ranges, image, contrib, final_tau, work_counter, st);
+  if (rc) return rc;
   int dev = 0, sms = 148;
   GSB_CUDA_TRY(cudaGetDevice(&dev));
   GSB_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));

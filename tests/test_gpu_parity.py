@@ -409,3 +409,14 @@ def test_reference_backward_gpu_script_unmodified():
     assert b["ng"] == 0 and b["ok"] == 19, b["lines"]
     f = res["forward_gpu"]
     assert f["image_shape"] == [3, 546, 979] and f["image_max"] > 0.1
+
+
+@pytest.mark.parametrize("N,W,H", [(2_000_000, 1920, 1080), (5_000_000, 3840, 2160)])
+def test_large_configs_vs_oracle(N, W, H):
+    """BASELINE config 5's scene size (2M Gaussians at 1080p) and config 4's largest corner
+    (5M at 4K: 32 400 tiles, 15 tile bits + 14 depth bits = 8-bit digits, 4 sort passes) against the
+    oracle at full size: culls, ranges and sort order bit-exact, image / gradients within the
+    BASELINE-shaped tolerances of run_splat_case."""
+    sc = synthetic_scene(N, W, H, sh_dim=12, seed=2)
+    sc, o, (image, contrib, ftau, ranges, gsid), ref = run_splat_case(N, W, H, sc=sc, seed=2)
+    assert 2.0 * N < gsid.numel() < 3.2 * N
