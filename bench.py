@@ -239,7 +239,7 @@ def run_ours(args, rank, world):
 
         def step_sel(dl):
             image, ctx = mv.render(cam)
-            mv.backward(ctx, dl)
+            mv.backward(ctx, dl, last=True)
             mv_out[0] = mv.reduce()
             return image
     else:
@@ -277,7 +277,7 @@ def run_ours(args, rank, world):
             img_host.copy_(img, non_blocking=True)
         main.wait_event(ev_dl)
         if world > 1:
-            mv.backward(ctx, dl_dev)
+            mv.backward(ctx, dl_dev, last=True)
             gp = mv.reduce()["dpws"]
         else:
             image.backward(dl_dev)
@@ -548,9 +548,9 @@ def run_config5(torch, dist, dev, rank, world, timed):
 
     def step():
         ev[0].record()
-        for cam in cams:
+        for i, cam in enumerate(cams):
             image, ctx = mv.render(cam)
-            mv.backward(ctx, dl)
+            mv.backward(ctx, dl, last=i == len(cams) - 1)
         ev[1].record()
         out[0] = mv.reduce()
         ev[2].record()

@@ -348,7 +348,7 @@ size_t gsb_splat_backward_workspace_bytes(int N, int H, int W, int64_t P) {
   // moment accumulators
   const size_t T = (size_t)((W + GSB_TILE - 1) / GSB_TILE) * (size_t)((H + GSB_TILE - 1) / GSB_TILE);
   return (size_t)(P > 0 && N > 0 ? N : 1) * sizeof(Rec) + 512 + (size_t)(N > 0 ? N : 1) * 9 * sizeof(float) + 512 +
-         (T + 2) * sizeof(int);  // + the rasterizer's work area
+         (4 * T + 2) * sizeof(int);  // + the rasterizer's work area
 }
 
 int gsb_splat_backward(int H, int W, int N, int64_t P, const float *us, const float *cinv2ds,

@@ -525,7 +525,7 @@ int sort_layout(int N, int H, int W, int64_t P, SortLayout *out) {
   L.vals_a = o; o = align_up(o + n * sizeof(int32_t), 256);
   L.vals_b = o; o = align_up(o + n * sizeof(int32_t), 256);
   L.recs = o;   o = align_up(o + ng * sizeof(Rec), 256);  // one record per Gaussian
-  L.counters = o; o = align_up(o + (T + 2) * sizeof(int), 256);  // rasterizer work area (launch_tile_list)
+  L.counters = o; o = align_up(o + (4 * T + 2) * sizeof(int), 256);  // rasterizer work area (launch_tile_list)
   // zeroed per call: [status | global digit histograms | per-tile digit counts of every pass]
   L.sort_state = o;
   L.hist = o + 64;

@@ -161,7 +161,7 @@ int launch_draw_bwd4_kernel(int H, int W, const int32_t *ranges, const Rec *recs
                             float *moments, int *work_counter, cudaStream_t st);
 int launch_draw(int H, int W, const int32_t *ranges, const Rec *recs, const int32_t *gsid, float *image,
                 int32_t *contrib, float *final_tau, int *tile_counter, int *work_counter, cudaStream_t st);
-// work = [item counter, #tiles with patches, their ids ...] (2 + tiles ints); with outputs given the
+// work = [item counter, #entries, entries ...] (2 + 4 * tiles ints, see k_tile_list); with outputs given the
 // empty tiles are zero-filled here
 int launch_tile_list(int H, int W, const int32_t *ranges, float *image, int32_t *contrib, float *final_tau,
                      int *work, cudaStream_t st);

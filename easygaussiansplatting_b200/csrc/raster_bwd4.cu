@@ -180,20 +180,44 @@ __global__ void __launch_bounds__(128, BWD4_MINBLOCKS) k_draw_bwd4(
   if (threadIdx.x < 12) reinterpret_cast<float *>(&s_dummy)[threadIdx.x] = 0.0f;
   __syncthreads();  // (the only CTA-wide barrier: start-up)
   (void)T;
-  const int items = 4 * work[1];  // 8x8 blocks of the tiles that have patches (k_tile_list, raster_fwd3.cu)
-  const int *__restrict__ tile_list = work + 2;
+  const int items = work[1];  // entries of the work list (k_tile_list, raster_fwd3.cu)
+  const int *__restrict__ entries = work + 2;
 
+  // One flat loop over 8x8 blocks: a new work-list entry is pulled when the current one is used up
+  // (an entry is one block of a dense tile, or all four blocks of a tile with <= 32 patches).
+  int tile = 0, len = 0, blk = 0, blk_end = 0;
+  bool whole_tile = false;
+  int2 range = make_int2(0, 0);
   for (;;) {
-    int item = 0;
-    if (lane == 0) item = atomicAdd(work, 1);
-    item = __shfl_sync(0xffffffffu, item, 0);
-    if (item >= items) break;
-    const int tile = __ldg(tile_list + (item >> 2)), blk = item & 3;
-    const int2 range = __ldg(ranges + tile);
-    const int len = range.y - range.x;
-    if (len <= 0) continue;
+    if (blk == blk_end) {
+      int item = 0;
+      if (lane == 0) item = atomicAdd(work, 1);
+      item = __shfl_sync(0xffffffffu, item, 0);
+      if (item >= items) break;
+      const int ent = __ldg(entries + item);
+      const int code = ent & 7;
+      tile = ent >> 3;
+      whole_tile = code == 4;  // <= 32 patches: all four blocks from one gather
+      range = __ldg(ranges + tile);
+      len = range.y - range.x;
+      if (len <= 0) continue;
+      blk = whole_tile ? 0 : code;
+      blk_end = whole_tile ? 4 : code + 1;
+      if (whole_tile) {  // the tile's single chunk, gathered once (two groups: see the wait below)
+        if (lane < len) {
+          const char *src = reinterpret_cast<const char *>(recs + __ldg(gsid + range.x + lane));
+          const uint32_t dst = ring_addr + lane * 48;
+          cp_async16_sa(dst, src);
+          cp_async16_sa(dst + 16, src + 16);
+          cp_async16_sa(dst + 32, src + 32);
+        }
+        cp_async_commit();
+        cp_async_commit();
+      }
+    }
+    const int cur = blk++;
     const int tx = tile % gx, ty = tile / gx;
-    const int rx0 = tx * TILE + (blk & 1) * 8, ry0 = ty * TILE + (blk >> 1) * 8;
+    const int rx0 = tx * TILE + (cur & 1) * 8, ry0 = ty * TILE + (cur >> 1) * 8;
     if (rx0 >= W || ry0 >= H) continue;  // block entirely outside the image
     const int px = rx0 + 2 * (lane & 3), py = ry0 + (lane >> 2);
     const bool in0 = px < W && py < H, in1 = px + 1 < W && py < H;
@@ -239,9 +263,12 @@ __global__ void __launch_bounds__(128, BWD4_MINBLOCKS) k_draw_bwd4(
       cp_async_commit();
     };
     auto load_id = [&](int c) { return (c >= 0 && c * 32 + lane < wmax) ? __ldg(ids + c * 32 + lane) : 0; };
+    int id_next = 0;
+    if (!whole_tile) {
 #pragma unroll
-    for (int r = 0; r < B4_RING; r++) issue(nch - 1 - r, load_id(nch - 1 - r));
-    int id_next = load_id(nch - 1 - B4_RING);  // id of the chunk the first refill gathers
+      for (int r = 0; r < B4_RING; r++) issue(nch - 1 - r, load_id(nch - 1 - r));
+      id_next = load_id(nch - 1 - B4_RING);  // id of the chunk the first refill gathers
+    }
 
     const float2 npx = p2(-(float)px, -(float)(px + 1));
     const float fpy = (float)py;
@@ -322,7 +349,7 @@ __global__ void __launch_bounds__(128, BWD4_MINBLOCKS) k_draw_bwd4(
       __syncwarp();
       b4_flush(w_addr, inf, dl_addr, (lane >> 2) - to_my_slot, bx0, by0, moments, lane);
     }
-    __syncwarp();  // the flush has read s_dl / s_w before the next item rewrites them
+    __syncwarp();  // the flush has read s_dl / s_w before the next block rewrites them
   }
 }
 

@@ -65,43 +65,78 @@ __device__ __forceinline__ float2 f3_alpha(const float4 &q0, const float4 &q1, c
 }
 }  // namespace
 
-// Work list of the two rasterizers: the tiles that have patches, compacted (work[1] = how many,
-// work[2..] = their ids; work[0] is the kernels' item counter).  A tile without patches keeps
+// Work list of the two rasterizers (work[0] = the kernels' item counter, work[1] = number of
+// entries, work[2..] = entries): a tile with more than 32 patches contributes four entries
+// `tile * 8 + block` (one 8x8 block each), a tile with 1..32 patches ONE entry `tile * 8 + 4` --
+// the warp that pulls it gathers the tile's single chunk of records once and renders all four
+// blocks from it (a block of a sparse tile is bounded by the latency of its queue pull, range
+// load, id load and gather, not by work: this quarters them).  A tile without patches keeps
 // image 0, contrib 0, tau 0 (kernel.cu:182-183): when outputs are given this pass writes those
-// zeros itself with 16-byte stores -- one warp per tile -- so the sparse corner of BASELINE config 4
+// zeros itself with 16-byte stores -- one warp per empty tile -- so the sparse corner of BASELINE config 4
 // (50k Gaussians at 4K: 32 400 tiles, most of them empty) costs one streaming pass over the
 // frame instead of one queue item per 8x8 block.
 __global__ void __launch_bounds__(256) k_tile_list(int W, int H, int gx, int T, const int2 *__restrict__ ranges,
                                                    float *__restrict__ image, int32_t *__restrict__ contrib,
                                                    float *__restrict__ final_tau, int *__restrict__ work) {
-  const int lane = threadIdx.x & 31;
-  const int tile = blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (tile >= T) return;
-  const int2 r = __ldg(ranges + tile);
-  if (r.y - r.x > 0) {
-    if (lane == 0) work[2 + atomicAdd(work + 1, 1)] = tile;
-    return;
+  __shared__ unsigned s_empty[8];  // per warp: which of its 32 tiles have no patches
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int tile = blockIdx.x * 256 + threadIdx.x;  // phase 1: one thread per tile
+  int len = 0;
+  if (tile < T) {
+    const int2 r = __ldg(ranges + tile);
+    len = r.y - r.x;
+  }
+  const bool has = len > 0;
+  const int n_ent = !has ? 0 : (len <= 32 ? 1 : 4);
+  int incl = n_ent;  // warp prefix sum of the entry counts -> one atomic per 32 tiles
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  const unsigned m = __ballot_sync(0xffffffffu, has);
+  int base = 0;
+  if (lane == 31 && incl) base = atomicAdd(work + 1, incl);
+  base = __shfl_sync(0xffffffffu, base, 31) + incl - n_ent;
+  if (n_ent == 1) work[2 + base] = tile * 8 + 4;
+  if (n_ent == 4) {
+#pragma unroll
+    for (int b = 0; b < 4; b++) work[2 + base + b] = tile * 8 + b;
   }
   if (image == nullptr) return;
+  if (lane == 0) s_empty[warp] = ~m;
+  __syncthreads();
+  // phase 2: the CTA's empty tiles, one warp per tile, 16-byte stores
   const size_t HW = (size_t)H * W;
-  const int x0 = (tile % gx) * TILE + (lane & 1) * 8, y = (tile / gx) * TILE + (lane >> 1);
-  if (y >= H || x0 >= W) return;
-  const size_t pix = (size_t)y * W + x0;
-  if ((W & 3) == 0 && x0 + 8 <= W) {  // 8 pixels = two 16-byte stores per plane
-    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int w = 0; w < 8; w++) {
+    unsigned e = s_empty[w];
+    // warp `warp` takes every 8th empty tile of the CTA's list; simple static split
+    for (int k = 0; e; k++) {
+      const int bit = __ffs(e) - 1;
+      e &= e - 1;
+      if ((k & 7) != warp) continue;
+      const int t = blockIdx.x * 256 + w * 32 + bit;
+      if (t >= T) break;
+      const int x0 = (t % gx) * TILE + (lane & 1) * 8, y = (t / gx) * TILE + (lane >> 1);
+      if (y >= H || x0 >= W) continue;
+      const size_t pix = (size_t)y * W + x0;
+      if ((W & 3) == 0 && x0 + 8 <= W) {  // 8 pixels = two 16-byte stores per plane
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-    for (int h = 0; h < 2; h++) {
-      *reinterpret_cast<float4 *>(image + pix + 4 * h) = z;
-      *reinterpret_cast<float4 *>(image + HW + pix + 4 * h) = z;
-      *reinterpret_cast<float4 *>(image + 2 * HW + pix + 4 * h) = z;
-      *reinterpret_cast<int4 *>(contrib + pix + 4 * h) = make_int4(0, 0, 0, 0);
-      *reinterpret_cast<float4 *>(final_tau + pix + 4 * h) = z;
-    }
-  } else {
-    for (int x = x0; x < min(x0 + 8, W); x++) {
-      const size_t q = (size_t)y * W + x;
-      image[q] = 0.f; image[HW + q] = 0.f; image[2 * HW + q] = 0.f;
-      contrib[q] = 0; final_tau[q] = 0.f;
+        for (int h = 0; h < 2; h++) {
+          *reinterpret_cast<float4 *>(image + pix + 4 * h) = z;
+          *reinterpret_cast<float4 *>(image + HW + pix + 4 * h) = z;
+          *reinterpret_cast<float4 *>(image + 2 * HW + pix + 4 * h) = z;
+          *reinterpret_cast<int4 *>(contrib + pix + 4 * h) = make_int4(0, 0, 0, 0);
+          *reinterpret_cast<float4 *>(final_tau + pix + 4 * h) = z;
+        }
+      } else {
+        for (int x = x0; x < min(x0 + 8, W); x++) {
+          const size_t q = (size_t)y * W + x;
+          image[q] = 0.f; image[HW + q] = 0.f; image[2 * HW + q] = 0.f;
+          contrib[q] = 0; final_tau[q] = 0.f;
+        }
+      }
     }
   }
 }
@@ -111,7 +146,7 @@ int launch_tile_list(int H, int W, const int32_t *ranges, float *image, int32_t 
   const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
   const int T = gx * gy;
   GSB_CUDA_TRY(cudaMemsetAsync(work, 0, 2 * sizeof(int), st));
-  k_tile_list<<<(T + 7) / 8, 256, 0, st>>>(W, H, gx, T, reinterpret_cast<const int2 *>(ranges), image, contrib,
+  k_tile_list<<<(T + 255) / 256, 256, 0, st>>>(W, H, gx, T, reinterpret_cast<const int2 *>(ranges), image, contrib,
                                            final_tau, work);
   GSB_CUDA_TRY(cudaGetLastError());
   return 0;
@@ -138,23 +173,37 @@ __global__ void __launch_bounds__(128, FWD3_MINBLOCKS) k_draw3(int W, int H, int
   if (threadIdx.x < 12) reinterpret_cast<float *>(&s_dummy)[threadIdx.x] = 0.0f;
   __syncthreads();  // (the only CTA-wide barrier: start-up)
   (void)T;
-  const int items = 4 * work[1];  // 8x8 blocks of the tiles that have patches (k_tile_list)
-  const int *__restrict__ tile_list = work + 2;
+  const int items = work[1];  // entries of the work list (k_tile_list)
+  const int *__restrict__ entries = work + 2;
 
   for (;;) {
     int item = 0;
     if (lane == 0) item = atomicAdd(work, 1);
     item = __shfl_sync(0xffffffffu, item, 0);
     if (item >= items) break;
-    const int tile = __ldg(tile_list + (item >> 2)), blk = item & 3;
+    const int ent = __ldg(entries + item);
+    const int tile = ent >> 3, code = ent & 7;
+    const bool whole_tile = code == 4;  // <= 32 patches: this warp renders all four blocks from one gather
+    const int2 range = __ldg(ranges + tile);
+    const int len = range.y - range.x;
+    if (whole_tile) {  // the tile's single chunk, gathered once (two groups: see the wait below)
+      if (lane < len) {
+        const char *src = reinterpret_cast<const char *>(recs + __ldg(gsid + range.x + lane));
+        const uint32_t dst = ring_addr + lane * 48;
+        cp_async16_sa(dst, src);
+        cp_async16_sa(dst + 16, src + 16);
+        cp_async16_sa(dst + 32, src + 32);
+      }
+      cp_async_commit();
+      cp_async_commit();
+    }
+   for (int blk = whole_tile ? 0 : code; blk < (whole_tile ? 4 : code + 1); blk++) {
     const int tx = tile % gx, ty = tile / gx;
     const int rx0 = tx * TILE + (blk & 1) * 8, ry0 = ty * TILE + (blk >> 1) * 8;
     if (rx0 >= W || ry0 >= H) continue;  // block entirely outside the image
     const int px = rx0 + 2 * (lane & 3), py = ry0 + (lane >> 2);
     const bool in0 = px < W && py < H, in1 = px + 1 < W && py < H;
     const size_t pix = (size_t)py * W + px;
-    const int2 range = __ldg(ranges + tile);
-    const int len = range.y - range.x;
 
     float2 tau = p2s(0.f), cr = p2s(0.f), cg = p2s(0.f), cb = p2s(0.f);
     int cont0 = 0, cont1 = 0;
@@ -172,9 +221,12 @@ __global__ void __launch_bounds__(128, FWD3_MINBLOCKS) k_draw3(int W, int H, int
         cp_async_commit();
       };
       auto load_id = [&](int c) { return (c < nch && c * 32 + lane < len) ? __ldg(ids + c * 32 + lane) : 0; };
+      int id_next = 0;
+      if (!whole_tile) {
 #pragma unroll
-      for (int r = 0; r < F3_RING; r++) issue(r, load_id(r));
-      int id_next = load_id(F3_RING);
+        for (int r = 0; r < F3_RING; r++) issue(r, load_id(r));
+        id_next = load_id(F3_RING);
+      }
 
       const float2 npx = p2(-(float)px, -(float)(px + 1));
       const float fpy = (float)py;
@@ -252,6 +304,7 @@ __global__ void __launch_bounds__(128, FWD3_MINBLOCKS) k_draw3(int W, int H, int
         contrib[pix + 1] = cont1; final_tau[pix + 1] = tau.y;
       }
     }
+   }  // blocks of the entry
   }
 }
 

@@ -258,6 +258,7 @@ class MultiViewStep:
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.k3 = shs.shape[1] // 3
         self._small, self._colors, self._twcs, self._dus = None, [], [], []
+        self._early = None
 
     def render(self, cam):
         from . import ops
@@ -268,13 +269,17 @@ class MultiViewStep:
                                                             colors, areas, records=records, capacity=True)
         return image, (cam, us, cinv2ds, depths, colors, contrib, final_tau, ranges, gsid)
 
-    def backward(self, ctx, dloss_dimage):
+    def backward(self, ctx, dloss_dimage, last=False):
+        """last=True (the rank's final view of the step): the all-gather of the views' dL/dcolor
+        starts here, right after the rasterizer backward, and runs under the per-Gaussian backward."""
         from . import ops
         cam, us, cinv2ds, depths, colors, contrib, final_tau, ranges, gsid = ctx
         moments = ops.splatB(cam.height, cam.width, us, cinv2ds, self.alphas, depths, colors, contrib, final_tau,
                              ranges, gsid, dloss_dimage, moments_only=True)
         self._colors.append(moments[:, 6:9])          # dL/dcolor of this view
         self._twcs.append(cam.twc.reshape(1, 3))
+        if last and self.world > 1:
+            self._early = _start_gathers(torch.stack(self._colors), torch.cat(self._twcs).contiguous(), self.group)
         gpw, _, gs, gq, dus, dal = ops.preprocessB(
             self.pws, self.rots, self.scales, self.shs, cam.Rcw, cam.tcw, cam.twc, cam.fx, cam.fy, cam.cx, cam.cy,
             cam.width, cam.height, None, None, None, moments=moments, cinv2ds=cinv2ds, compact=True)
@@ -285,18 +290,34 @@ class MultiViewStep:
     def reduce(self):
         from . import ops
         N = self.pws.shape[0]
-        colors = torch.stack(self._colors)                       # [V_local, N, 3] (contiguous copy)
-        twcs = torch.cat(self._twcs).contiguous()                # [V_local, 3]
-        small, dshs = factorised_sum(self._small, colors, twcs, self.group,
-                                     lambda tw, col: ops.sh_grad_expand(self.pws, tw, col, self.k3))
+        expand = lambda tw, col: ops.sh_grad_expand(self.pws, tw, col, self.k3)
+        if self._early is not None:
+            colors = self._early[0]
+            small, dshs = factorised_sum(self._small, None, None, self.group, expand, started=self._early)
+        else:
+            colors = torch.stack(self._colors)                   # [V_local, N, 3] (contiguous copy)
+            twcs = torch.cat(self._twcs).contiguous()            # [V_local, 3]
+            small, dshs = factorised_sum(self._small, colors, twcs, self.group, expand)
         out = {"dpws": small[:3 * N].view(N, 3), "dscales": small[3 * N:6 * N].view(N, 3),
                "drots": small[6 * N:10 * N].view(N, 4), "dalphas": small[10 * N:], "dshs": dshs, "dus": self._dus,
                "bytes_per_rank": int(small.numel() * 4 + colors.numel() * 4)}
         self._small, self._colors, self._twcs, self._dus = None, [], [], []
+        self._early = None
         return out
 
 
-def factorised_sum(small, colors, twcs, group, expand):
+def _start_gathers(colors, twcs, group):
+    """-> (colors, all_colors, all_twcs, work handles): the two all-gathers of factorised_sum, started"""
+    world = dist.get_world_size(group)
+    N = colors.shape[1]
+    all_colors = torch.empty((world * colors.shape[0], N, 3), dtype=colors.dtype, device=colors.device)
+    all_twcs = torch.empty((world * twcs.shape[0], 3), dtype=twcs.dtype, device=twcs.device)
+    w1 = dist.all_gather_into_tensor(all_twcs, twcs, group=group, async_op=True)
+    w2 = dist.all_gather_into_tensor(all_colors, colors, group=group, async_op=True)
+    return colors, all_colors, all_twcs, (w1, w2)
+
+
+def factorised_sum(small, colors, twcs, group, expand, started=None):
     """The collective part of MultiViewStep.reduce: `small` (flat 11 N bucket) is summed over the
     ranks in place, `colors[V_local, N, 3]` / `twcs[V_local, 3]` are gathered from every rank (rank
     order, then local view order) and `expand(all_twcs, all_colors)` -> dL/dsh runs while the
@@ -304,11 +325,7 @@ def factorised_sum(small, colors, twcs, group, expand):
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     if world == 1:
         return small, expand(twcs, colors)
-    N = colors.shape[1]
-    all_colors = torch.empty((world * colors.shape[0], N, 3), dtype=colors.dtype, device=colors.device)
-    all_twcs = torch.empty((world * twcs.shape[0], 3), dtype=twcs.dtype, device=twcs.device)
-    w1 = dist.all_gather_into_tensor(all_twcs, twcs, group=group, async_op=True)
-    w2 = dist.all_gather_into_tensor(all_colors, colors, group=group, async_op=True)
+    _, all_colors, all_twcs, (w1, w2) = started if started is not None else _start_gathers(colors, twcs, group)
     w3 = dist.all_reduce(small, op=dist.ReduceOp.SUM, group=group, async_op=True)
     w1.wait(); w2.wait()  # stream-ordered waits on NCCL; the all-reduce runs under the expansion
     dshs = expand(all_twcs, all_colors)
