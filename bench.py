@@ -369,6 +369,25 @@ def run_ours(args, rank, world):
         lib.gsb_profile_read(i, C.byref(ms_tot), C.byref(cnt))
         if cnt.value:
             kern[lib.gsb_profile_kernel_name(i).decode()] = ms_tot.value / prof_steps
+    # ---- the same single-view step replayed as two CUDA graphs (graphed.GraphedFusedStep)
+    graphs = None
+    if rank == 0:
+        try:
+            from easygaussiansplatting_b200.graphed import GraphedFusedStep
+            gstep = GraphedFusedStep(params["pws"], params["shs"], alphas, params["scales"], params["rots"], cam)
+
+            def graphed_step():
+                gstep.forward()
+                gstep.dloss_dimage.copy_(dl_dev)
+                gstep.backward()
+            ms_g = timed(graphed_step, args.steps, 3, collective=False) / args.steps
+            graphs = {"what": "forward and backward of this rank's view replayed as CUDA graphs over static buffers "
+                              "(capacity-based rasterizer, lazily validated status; dL/dimage copied in between); "
+                              "the kernels are launched by the graph, so `gpu_launches` does not see them",
+                      "ms_per_step": ms_g, "value": WIDTH * HEIGHT / (ms_g * 1e-3) / 1e6, "unit": "Mpixels/s"}
+            del gstep
+        except Exception as e:  # noqa: BLE001
+            graphs = {"error": repr(e)[:200]}
     config5 = run_config5(torch, dist, dev, rank, world, timed)
     if rank != 0:
         if world > 1:
@@ -515,6 +534,7 @@ def run_ours(args, rank, world):
         "clocks": clocks,
     }
     line["config5"] = config5
+    line["cuda_graphs"] = graphs
     if allreduce is not None:
         line["allreduce"] = allreduce
     print(json.dumps(line))

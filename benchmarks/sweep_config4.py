@@ -74,10 +74,31 @@ def main():
                 pad[:H, :W] = o[1]
                 p_eff = int(pad.view(gy, 16, gx, 16).amax(dim=(1, 3)).sum().item())
             t = statistics.median(ms)
+            # the same step replayed as two CUDA graphs (graphed.GraphedFusedStep): no launch / wrapper cost
+            t_graph = None
+            try:
+                from easygaussiansplatting_b200.graphed import GraphedFusedStep
+                gstep = GraphedFusedStep(P["pws"], P["shs"], al, P["scales"], P["rots"], cam)
+
+                def gs():
+                    gstep.forward()
+                    gstep.dloss_dimage.copy_(dl)
+                    gstep.backward()
+                msg = []
+                for it in range(3 + a.iters):
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record(); gs(); e1.record(); torch.cuda.synchronize()
+                    if it >= 3:
+                        msg.append(e0.elapsed_time(e1))
+                t_graph = statistics.median(msg)
+                del gstep
+            except Exception as e:  # noqa: BLE001 - the eager numbers stand on their own
+                t_graph = "failed: %r" % (e,)
             alg_f = 44 * p_eff + 8 * gx * gy + 20 * W * H
             alg_b = alg_f + 36 * N
             row = dict(N=N, W=W, H=H, patches=npatch, patches_per_tile=npatch / (gx * gy), p_eff=p_eff,
-                       ms_per_step=t, mpix_per_s=W * H / (t * 1e-3) / 1e6, gaussians_per_s=N / (t * 1e-3),
+                       ms_per_step=t, ms_per_step_cuda_graphs=t_graph, mpix_per_s=W * H / (t * 1e-3) / 1e6,
+                       gaussians_per_s=N / (t * 1e-3),
                        kernel_ms=kern,
                        draw_hbm_frac=alg_f / (kern["draw"] * 1e-3) / 1e9 / hbm,
                        draw_backward_hbm_frac=alg_b / (kern["draw_backward"] * 1e-3) / 1e9 / hbm,

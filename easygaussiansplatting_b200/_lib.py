@@ -39,6 +39,8 @@ SIGNATURES = {
     "gsb_splat_backward_workspace_bytes": (_sz, [_i, _i, _i, _i64]),
     "gsb_splat_forward": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, C.c_uint32, _vp, _sz, _vp, _sz,
                                _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "gsb_splat_forward_enqueue": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, C.c_uint32, _vp, _sz, _vp,
+                                       _sz, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gsb_splat_backward": (_i, [_i, _i, _i, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                 _sz, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gsb_sh_grad_expand": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp]),

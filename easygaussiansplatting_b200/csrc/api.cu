@@ -289,12 +289,12 @@ int gsb_splat_render(int H, int W, int N, int64_t P, uint32_t depth_key_max, con
                      work_counter, st);
 }
 
-int gsb_splat_forward(int H, int W, int N, const float *us, const float *cinv2ds, const float *alphas,
-                      float *depths, const float *colors, int32_t *areas, const void *packed_records,
-                      int64_t P_cap, uint32_t depth_key_cap, void *bin_ws, size_t bin_ws_bytes, void *ws,
-                      size_t ws_bytes, float *image, int32_t *contrib, float *final_tau,
-                      int32_t *patch_range_per_tile, int32_t *gsid_per_patch, uint32_t *status_host,
-                      gsb_stream_t stream) {
+static int splat_forward_impl(int H, int W, int N, const float *us, const float *cinv2ds, const float *alphas,
+                              float *depths, const float *colors, int32_t *areas, const void *packed_records,
+                              int64_t P_cap, uint32_t depth_key_cap, void *bin_ws, size_t bin_ws_bytes, void *ws,
+                              size_t ws_bytes, float *image, int32_t *contrib, float *final_tau,
+                              int32_t *patch_range_per_tile, int32_t *gsid_per_patch, uint32_t *status_host,
+                              gsb_stream_t stream, bool wait) {
   GSB_REQUIRE(N >= 0 && H > 0 && W > 0 && P_cap > 0 && P_cap < ((int64_t)1 << 30), "splat_forward: bad N/H/W/P_cap");
   GSB_REQUIRE(image && contrib && final_tau && patch_range_per_tile && gsid_per_patch && status_host && bin_ws && ws,
               "splat_forward: null pointer");
@@ -307,10 +307,11 @@ int gsb_splat_forward(int H, int W, int N, const float *us, const float *cinv2ds
   int rc = sort_layout(N, H, W, P_cap, &SL);
   if (rc) return rc;
   GSB_REQUIRE(ws_bytes >= SL.bytes, "splat_forward: workspace too small");
-  static thread_local cudaEvent_t ready = nullptr;
-  if (ready == nullptr) GSB_CUDA_TRY(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+  static thread_local cudaEvent_t ready_ev = nullptr;
+  if (wait && ready_ev == nullptr) GSB_CUDA_TRY(cudaEventCreateWithFlags(&ready_ev, cudaEventDisableTiming));
+  cudaEvent_t ready = wait ? ready_ev : nullptr;
   const StatusRead sr{status_host, ready};
-  status_host[0] = status_host[1] = status_host[2] = 0;
+  if (wait) status_host[0] = status_host[1] = status_host[2] = 0;
   rc = launch_bin(H, W, N, us, depths, areas, bin_ws, BL, st);
   if (rc) return rc;
   if (N == 0) {  // nothing to bin: every tile is empty
@@ -332,6 +333,7 @@ int gsb_splat_forward(int H, int W, int N, const float *us, const float *cinv2ds
   rc = launch_draw(H, W, patch_range_per_tile, recs, gsid_per_patch, image, contrib, final_tau, tile_counter,
                    work_counter, st);
   if (rc) return rc;
+  if (!wait) return 0;  // enqueue-only (CUDA graph capture): the caller inspects status_host later
   // the sort and the rasterizer are queued; now look at what the binning found
   GSB_CUDA_TRY(cudaEventSynchronize(ready));
   if ((status_host[2] & 1u) != 0 || status_host[0] >= (1u << 30)) return set_arg_error("splat: more than 2^30 patches");
@@ -341,6 +343,28 @@ int gsb_splat_forward(int H, int W, int N, const float *us, const float *cinv2ds
     return GSB_CAPACITY_EXCEEDED;
   }
   return 0;
+}
+
+int gsb_splat_forward(int H, int W, int N, const float *us, const float *cinv2ds, const float *alphas,
+                      float *depths, const float *colors, int32_t *areas, const void *packed_records,
+                      int64_t P_cap, uint32_t depth_key_cap, void *bin_ws, size_t bin_ws_bytes, void *ws,
+                      size_t ws_bytes, float *image, int32_t *contrib, float *final_tau,
+                      int32_t *patch_range_per_tile, int32_t *gsid_per_patch, uint32_t *status_host,
+                      gsb_stream_t stream) {
+  return splat_forward_impl(H, W, N, us, cinv2ds, alphas, depths, colors, areas, packed_records, P_cap, depth_key_cap,
+                            bin_ws, bin_ws_bytes, ws, ws_bytes, image, contrib, final_tau, patch_range_per_tile,
+                            gsid_per_patch, status_host, stream, true);
+}
+
+int gsb_splat_forward_enqueue(int H, int W, int N, const float *us, const float *cinv2ds, const float *alphas,
+                              float *depths, const float *colors, int32_t *areas, const void *packed_records,
+                              int64_t P_cap, uint32_t depth_key_cap, void *bin_ws, size_t bin_ws_bytes, void *ws,
+                              size_t ws_bytes, float *image, int32_t *contrib, float *final_tau,
+                              int32_t *patch_range_per_tile, int32_t *gsid_per_patch, uint32_t *status_host,
+                              gsb_stream_t stream) {
+  return splat_forward_impl(H, W, N, us, cinv2ds, alphas, depths, colors, areas, packed_records, P_cap, depth_key_cap,
+                            bin_ws, bin_ws_bytes, ws, ws_bytes, image, contrib, final_tau, patch_range_per_tile,
+                            gsid_per_patch, status_host, stream, false);
 }
 
 size_t gsb_splat_backward_workspace_bytes(int N, int H, int W, int64_t P) {

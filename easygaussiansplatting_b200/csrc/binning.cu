@@ -580,7 +580,7 @@ static int keys_sort_ranges(int N, int64_t P_cap, const float *depths, const uin
   if (sr != nullptr) {  // everything the host has to validate is known now; the sort and the
     // rasterizer are enqueued behind this copy and run while the host waits for it
     GSB_CUDA_TRY(cudaMemcpyAsync(sr->host, total, 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-    GSB_CUDA_TRY(cudaEventRecord(sr->ready, st));
+    if (sr->ready != nullptr) GSB_CUDA_TRY(cudaEventRecord(sr->ready, st));
   }
   {
     ProfScope ps(K_SORT, st);

@@ -170,6 +170,16 @@ int gsb_splat_forward(int H, int W, int N, const float *us, const float *cinv2ds
                       int32_t *patch_range_per_tile, int32_t *gsid_per_patch, uint32_t *status_host,
                       gsb_stream_t stream);
 
+/* Same, but only ENQUEUES (no host wait, no event): for capture into a CUDA graph.  status_host is
+ * written by a stream-ordered copy; the caller reads it after the work has completed (flags bit 1:
+ * P_cap exceeded, bit 2: depth_key_cap exceeded, or P > P_cap -> the frame's outputs are invalid). */
+int gsb_splat_forward_enqueue(int H, int W, int N, const float *us, const float *cinv2ds, const float *alphas,
+                              float *depths, const float *colors, int32_t *areas, const void *packed_records,
+                              int64_t P_cap, uint32_t depth_key_cap, void *bin_ws, size_t bin_ws_bytes, void *ws,
+                              size_t ws_bytes, float *image, int32_t *contrib, float *final_tau,
+                              int32_t *patch_range_per_tile, int32_t *gsid_per_patch, uint32_t *status_host,
+                              gsb_stream_t stream);
+
 /* ---- splatB.  Replaces `splatB` (ext.cpp:20-32, gausplat.cu:114-159, kernel.cu:809-950).
  * Consumes the forward's contrib / final_tau / patch_range_per_tile / gsid_per_patch.
  * -> dloss_dus[N,1,2], dloss_dcinv2ds[N,1,3], dloss_dalphas[N,1,1], dloss_dcolors[N,1,3]

@@ -301,3 +301,49 @@ def test_factorised_multi_view_step_matches_autograd_accumulation(N, W, H, sh_di
         got = g[name].reshape(want.shape)
         err = float((got - want).abs().max() / want.abs().max().clamp_min(1e-30))
         assert err <= 2e-6, (name, err)
+
+
+def test_graphed_step_matches_eager_and_detects_overflow():
+    """graphed.GraphedFusedStep (forward and backward replayed as CUDA graphs over static buffers,
+    capacity-based rasterizer, lazily checked status) against the eager fused autograd path; new
+    parameter values written in place are seen by the next replay; a frame that outgrows the
+    captured capacity raises CapacityError."""
+    from easygaussiansplatting_b200.graphed import CapacityError, GraphedFusedStep
+    from easygaussiansplatting_b200.gsfunction import Camera, GSFunctionFused
+    N, W, H, sh_dim = 20000, 320, 240, 12
+    sc = scene(N, W, H, sh_dim, 6)
+    P = {k: t(sc[k]).requires_grad_() for k in ("pws", "shs", "scales", "rots")}
+    al = t(sc["alphas"][:, None]).requires_grad_()
+    us0 = torch.zeros((N, 2), device=DEV, requires_grad=True)
+    cam = Camera(W, H, sc["fx"], sc["fy"], sc["cx"], sc["cy"], t(sc["Rcw"]), t(sc["tcw"]), t(sc["twc"]))
+    dl = t(upstream_gradient(W, H, 1) * (3.0 * W * H))
+    step = GraphedFusedStep(P["pws"], P["shs"], al, P["scales"], P["rots"], cam)
+
+    def eager():
+        for p in list(P.values()) + [al]:
+            p.grad = None
+        image, _ = GSFunctionFused.apply(P["pws"], P["shs"], al, P["scales"], P["rots"], us0, cam)
+        image.backward(dl)
+        return image.detach()
+
+    for rep in range(2):
+        want = eager()
+        img = step.forward()
+        assert torch.equal(img, want)
+        step.dloss_dimage.copy_(dl)
+        g = step.backward()
+        for name, ref in (("dpws", P["pws"].grad), ("dshs", P["shs"].grad), ("dscales", P["scales"].grad),
+                          ("drots", P["rots"].grad), ("dalphas", al.grad.reshape(-1))):
+            err = float((g[name].reshape(ref.shape) - ref).abs().max() / ref.abs().max().clamp_min(1e-30))
+            assert err <= 2e-6, (name, err)
+        with torch.no_grad():  # an in-place parameter update is picked up by the next replay
+            P["pws"].add_(0.01 * torch.randn_like(P["pws"]))
+            P["scales"].mul_(1.05)
+    # blow the scene up so that the patch count exceeds the captured capacity
+    with torch.no_grad():
+        P["scales"].mul_(4.0)
+    step.forward()
+    with pytest.raises(CapacityError):
+        step.backward()
+    step.recapture()
+    assert torch.equal(step.forward(), eager())
