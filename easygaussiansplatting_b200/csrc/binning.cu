@@ -339,8 +339,14 @@ __global__ void __launch_bounds__(1024) k_colscan(const uint32_t *__restrict__ P
   }
 }
 
+#ifndef RX_UNROLL_OUT
+#define RX_UNROLL_OUT 0
+#endif
+#ifndef RX_MINBLOCKS
+#define RX_MINBLOCKS 3
+#endif
 template <typename KeyT, int BITS>
-__global__ void __launch_bounds__(RX_THREADS, 2) k_radix_pass(const KeyT *__restrict__ keys_in,
+__global__ void __launch_bounds__(RX_THREADS, sizeof(KeyT) == 8 ? 2 : RX_MINBLOCKS) k_radix_pass(const KeyT *__restrict__ keys_in,
                                                               const int32_t *__restrict__ vals_in,
                                                               KeyT *__restrict__ keys_out,
                                                               int32_t *__restrict__ vals_out,
@@ -365,13 +371,11 @@ __global__ void __launch_bounds__(RX_THREADS, 2) k_radix_pass(const KeyT *__rest
     const uint32_t first = (uint32_t)tile * RX_TILE + warp * (32 * RX_IPT) + lane;
     const uint32_t tile_n = min((uint32_t)RX_TILE, P - (uint32_t)tile * RX_TILE);
     KeyT key[RX_IPT];
-    int32_t val[RX_IPT];
     uint32_t rank[RX_IPT];
 #pragma unroll
     for (int r = 0; r < RX_IPT; r++) {
       const uint32_t idx = first + r * 32;
       key[r] = idx < P ? keys_in[idx] : (KeyT)0;
-      val[r] = idx < P ? vals_in[idx] : 0;
     }
 #pragma unroll
     for (int r = 0; r < RX_IPT; r++) {
@@ -437,10 +441,11 @@ __global__ void __launch_bounds__(RX_THREADS, 2) k_radix_pass(const KeyT *__rest
       if (first + r * 32 < P) {
         const uint32_t lp = s_whist[warp][(uint32_t)(key[r] >> shift) & (BINS - 1)] + rank[r];
         s_keys[lp] = key[r];
-        s_vals[lp] = val[r];
+        s_vals[lp] = vals_in[first + r * 32];  // (read here, not held in registers through the ranking)
       }
     }
     __syncthreads();
+#if !RX_UNROLL_OUT
     for (uint32_t j = tid; j < tile_n; j += RX_THREADS) {  // sorted order: runs of equal digits are contiguous
       const KeyT k = s_keys[j];
       const uint32_t pos = s_gofs[(uint32_t)(k >> shift) & (BINS - 1)] + j;
@@ -449,6 +454,29 @@ __global__ void __launch_bounds__(RX_THREADS, 2) k_radix_pass(const KeyT *__rest
       if (next_C != nullptr)
         atomicAdd(next_C + (size_t)(pos / RX_TILE) * BINS + ((uint32_t)(k >> next_shift) & (BINS - 1)), 1u);
     }
+#else
+    {  // sorted order: runs of equal digits are contiguous.  Unrolled: 16 independent LDS -> STG chains
+      KeyT ko[RX_IPT];
+      int32_t vo[RX_IPT];
+#pragma unroll
+      for (int r = 0; r < RX_IPT; r++) {
+        const uint32_t j = tid + r * RX_THREADS;
+        ko[r] = j < tile_n ? s_keys[j] : (KeyT)0;
+        vo[r] = j < tile_n ? s_vals[j] : 0;
+      }
+#pragma unroll
+      for (int r = 0; r < RX_IPT; r++) {
+        const uint32_t j = tid + r * RX_THREADS;
+        if (j < tile_n) {
+          const uint32_t pos = s_gofs[(uint32_t)(ko[r] >> shift) & (BINS - 1)] + j;
+          keys_out[pos] = ko[r];
+          vals_out[pos] = vo[r];
+          if (next_C != nullptr)
+            atomicAdd(next_C + (size_t)(pos / RX_TILE) * BINS + ((uint32_t)(ko[r] >> next_shift) & (BINS - 1)), 1u);
+        }
+      }
+    }
+#endif
   }
 }
 
