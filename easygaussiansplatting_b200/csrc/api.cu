@@ -36,7 +36,7 @@ static const char *const g_names[K_COUNT] = {"project", "computeCov3D", "compute
                                              "preprocess_forward", "preprocess_backward",
                                              "finalize_splat_grads", "gau_loss_forward", "gau_loss_backward",
                                              "small_bmm", "density_accumulate", "density_classify",
-                                             "density_scan(cub)", "density_apply", "reset_alpha",
+                                             "density_scan", "density_apply", "reset_alpha",
                                              "ply_rows_to_gs", "gs_to_params", "params_to_gs",
                                              "grad_reduce_broadcast", "sh_grad_expand"};
 

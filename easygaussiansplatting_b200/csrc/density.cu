@@ -20,8 +20,14 @@
 #include <cub/device/device_scan.cuh>
 #include <thrust/iterator/transform_iterator.h>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "kernels.h"
+
+#ifndef GSB_DENSITY_DEFAULT_VARIANT
+#define GSB_DENSITY_DEFAULT_VARIANT 0
+#endif
 
 namespace gsb {
 
@@ -63,12 +69,10 @@ __global__ void k_density_accumulate(int64_t N, const float2 *__restrict__ dus, 
 }
 
 // gsmodel.py:238-262
-__global__ void k_density_classify(int64_t N, const float *__restrict__ alphas_raw,
-                                   const float *__restrict__ scales_raw, const float *__restrict__ acc,
-                                   const int32_t *__restrict__ cnt, float alpha_raw_min, float scale_raw_max,
-                                   float grad_min, float scale_clone_max, uint8_t *__restrict__ cls) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= N) return;
+__device__ __forceinline__ uint8_t classify_row(int64_t i, const float *__restrict__ alphas_raw,
+                                                const float *__restrict__ scales_raw, const float *__restrict__ acc,
+                                                const int32_t *__restrict__ cnt, float alpha_raw_min,
+                                                float scale_raw_max, float grad_min, float scale_clone_max) {
   const float a = alphas_raw[i];
   const float s0 = scales_raw[3 * i], s1 = scales_raw[3 * i + 1], s2 = scales_raw[3 * i + 2];
   const float smax = fmaxf(s0, fmaxf(s1, s2));
@@ -82,7 +86,130 @@ __global__ void k_density_classify(int64_t N, const float *__restrict__ alphas_r
     const float big = fmaxf(expf(s0), fmaxf(expf(s1), expf(s2)));
     c = g >= grad_min ? (big <= scale_clone_max ? CLS_CLONE : CLS_SPLIT) : CLS_KEEP;
   }
-  cls[i] = c;
+  return c;
+}
+
+__global__ void k_density_classify(int64_t N, const float *__restrict__ alphas_raw,
+                                   const float *__restrict__ scales_raw, const float *__restrict__ acc,
+                                   const int32_t *__restrict__ cnt, float alpha_raw_min, float scale_raw_max,
+                                   float grad_min, float scale_clone_max, uint8_t *__restrict__ cls) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  cls[i] = classify_row(i, alphas_raw, scales_raw, acc, cnt, alpha_raw_min, scale_raw_max, grad_min, scale_clone_max);
+}
+
+// ---- the slots (exclusive scan of the three class counters in row order), hand-written:
+//   k_density_classify_count  classify 2048 rows per CTA and leave the CTA's three counts;
+//   k_density_scan_blocks     one CTA turns the per-CTA counts into exclusive offsets + totals;
+//   k_density_slots           every CTA re-reads its 2048 class bytes (8 consecutive rows per
+//                             thread), scans them locally and writes the 12-byte slots.
+// 25 B per Gaussian in total; the three launches replace cub::DeviceScan over a 12-byte struct.
+constexpr int SC_THREADS = 256, SC_PER = 8, SC_ROWS = SC_THREADS * SC_PER;
+
+__global__ void __launch_bounds__(SC_THREADS) k_density_classify_count(
+    int64_t N, const float *__restrict__ alphas_raw, const float *__restrict__ scales_raw,
+    const float *__restrict__ acc, const int32_t *__restrict__ cnt, float alpha_raw_min, float scale_raw_max,
+    float grad_min, float scale_clone_max, uint8_t *__restrict__ cls, int32_t *__restrict__ block_counts) {
+  __shared__ uint32_t red[2][SC_THREADS / 32];
+  uint32_t kc = 0, sp = 0;  // (survivors | clones << 16), splits: at most 2048 each per CTA
+#pragma unroll
+  for (int j = 0; j < SC_PER; j++) {
+    const int64_t i = (int64_t)blockIdx.x * SC_ROWS + j * SC_THREADS + threadIdx.x;
+    if (i < N) {
+      const uint8_t c =
+          classify_row(i, alphas_raw, scales_raw, acc, cnt, alpha_raw_min, scale_raw_max, grad_min, scale_clone_max);
+      cls[i] = c;
+      kc += (c != CLS_PRUNE) + ((uint32_t)(c == CLS_CLONE) << 16);
+      sp += c == CLS_SPLIT;
+    }
+  }
+  kc = __reduce_add_sync(0xffffffffu, kc);
+  sp = __reduce_add_sync(0xffffffffu, sp);
+  if ((threadIdx.x & 31) == 0) red[0][threadIdx.x >> 5] = kc, red[1][threadIdx.x >> 5] = sp;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t a = 0, b = 0;
+#pragma unroll
+    for (int w = 0; w < SC_THREADS / 32; w++) a += red[0][w], b += red[1][w];
+    block_counts[3 * blockIdx.x + 0] = (int32_t)(a & 0xffffu);
+    block_counts[3 * blockIdx.x + 1] = (int32_t)(a >> 16);
+    block_counts[3 * blockIdx.x + 2] = (int32_t)b;
+  }
+}
+
+// in place: block_counts[b] -> the counts before CTA b; totals = the three sums
+__global__ void __launch_bounds__(1024) k_density_scan_blocks(int nb, int32_t *__restrict__ block_counts,
+                                                              int64_t *__restrict__ totals) {
+  __shared__ int warp_tot[3][32];
+  __shared__ int carry[3];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (threadIdx.x < 3) carry[threadIdx.x] = 0;
+  __syncthreads();
+  for (int base = 0; base < nb; base += 1024) {
+    const int b = base + threadIdx.x;
+    int v[3] = {0, 0, 0}, inc[3];
+    if (b < nb) v[0] = block_counts[3 * b], v[1] = block_counts[3 * b + 1], v[2] = block_counts[3 * b + 2];
+#pragma unroll
+    for (int q = 0; q < 3; q++) {
+      int x = v[q];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+      }
+      inc[q] = x;
+      if (lane == 31) warp_tot[q][wid] = x;
+    }
+    __syncthreads();
+    int c0[3];
+#pragma unroll
+    for (int q = 0; q < 3; q++) {
+      int before = carry[q];
+      for (int w = 0; w < wid; w++) before += warp_tot[q][w];
+      c0[q] = before + inc[q] - v[q];
+    }
+    if (b < nb) block_counts[3 * b] = c0[0], block_counts[3 * b + 1] = c0[1], block_counts[3 * b + 2] = c0[2];
+    __syncthreads();
+    if (threadIdx.x == 1023) {
+#pragma unroll
+      for (int q = 0; q < 3; q++) carry[q] = c0[q] + v[q];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x < 3) totals[threadIdx.x] = carry[threadIdx.x];
+}
+
+__global__ void __launch_bounds__(SC_THREADS) k_density_slots(int64_t N, const uint8_t *__restrict__ cls,
+                                                              const int32_t *__restrict__ block_offsets,
+                                                              Slot3 *__restrict__ slots) {
+  __shared__ uint32_t warp_tot[2][SC_THREADS / 32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int64_t row0 = (int64_t)blockIdx.x * SC_ROWS + (int64_t)threadIdx.x * SC_PER;
+  uint8_t c[SC_PER];
+  uint32_t kc = 0, sp = 0;
+#pragma unroll
+  for (int j = 0; j < SC_PER; j++) {
+    c[j] = row0 + j < N ? cls[row0 + j] : (uint8_t)CLS_PRUNE;
+    kc += (c[j] != CLS_PRUNE) + ((uint32_t)(c[j] == CLS_CLONE) << 16);
+    sp += c[j] == CLS_SPLIT;
+  }
+  uint32_t ikc = kc, isp = sp;  // inclusive over the warp
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t a = __shfl_up_sync(0xffffffffu, ikc, o), b = __shfl_up_sync(0xffffffffu, isp, o);
+    if (lane >= o) ikc += a, isp += b;
+  }
+  if (lane == 31) warp_tot[0][wid] = ikc, warp_tot[1][wid] = isp;
+  __syncthreads();
+  uint32_t bkc = ikc - kc, bsp = isp - sp;  // exclusive within the CTA
+  for (int w = 0; w < wid; w++) bkc += warp_tot[0][w], bsp += warp_tot[1][w];
+  Slot3 run{block_offsets[3 * blockIdx.x] + (int)(bkc & 0xffffu), block_offsets[3 * blockIdx.x + 1] + (int)(bkc >> 16),
+            block_offsets[3 * blockIdx.x + 2] + (int)bsp};
+#pragma unroll
+  for (int j = 0; j < SC_PER; j++) {
+    if (row0 + j < N) slots[row0 + j] = run;
+    run.k += c[j] != CLS_PRUNE, run.c += c[j] == CLS_CLONE, run.s += c[j] == CLS_SPLIT;
+  }
 }
 
 __global__ void k_density_totals(int64_t N, const uint8_t *__restrict__ cls, const Slot3 *__restrict__ slots,
@@ -199,6 +326,133 @@ __global__ void __launch_bounds__(256) k_density_apply(I N, const uint8_t *__res
 #undef GSB_JOB
 }
 
+// ---- row-group variant (default for N < 23 M): a warp moves 32 consecutive Gaussians of one array.
+// The per-Gaussian plan (class, survivor slot, new-row slot) is read once per group into a
+// 32-entry shared-memory table instead of once per element (13 B per 4-byte element in the
+// kernel above); the group's source span of every array is 128 w bytes, 16-byte aligned, so
+// it is read with float4 loads, two in flight per lane; one division per float4.  Spans that
+// belong to pruned Gaussians only are not loaded.  Stores stay 4-byte (destination rows of a
+// compacted [*, 45] or [*, 3] array are only 4-byte aligned).
+constexpr int DG_WARPS = 8;
+
+// the value a clone / split writes at its new row (parameters; Adam moments start at 0)
+template <int A>
+__device__ __forceinline__ float new_row_value(float val, bool split, int64_t i, int s, int c, const Sets &S,
+                                               const float *__restrict__ z) {
+  float nv = val;
+  if (A == 0) {
+    if (split) nv += split_offset(S.p[5] + 4 * i, S.p[4] + 3 * i, z + 3 * (int64_t)s, c);
+  } else if (A == 3) {
+    nv = logit_of_sigmoid(nv);
+  } else if (A == 4) {
+    const float e = expf(nv);          // get_scales
+    nv = logf(split ? e * 0.6f : e);   // gsmodel.py:281 then get_scales_raw
+  } else if (A == 5) {
+    const float *q = S.p[5] + 4 * i;
+    nv = nv / fmaxf(sqrtf(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]), 1e-12f);
+  }
+  return nv;
+}
+
+template <int A, int SET>
+__device__ __forceinline__ void rows_job(int row0, int rows_here, const int2 *__restrict__ tab, int K, int C,
+                                         const Sets &S, const float *__restrict__ z, int lane) {
+  constexpr int w = kWidth[A];
+  const float *__restrict__ src = SET == 0 ? S.p[A] : (SET == 1 ? S.m[A] : S.v[A]);
+  float *__restrict__ dst = SET == 0 ? S.dp[A] : (SET == 1 ? S.dm[A] : S.dv[A]);
+  if (src == nullptr) return;
+  const float *__restrict__ gsrc = src + (size_t)row0 * w;
+  // element (row r of the group, column col) with plan entry `info`
+  auto emit = [&](int r, int col, int2 info, float val) {
+    const unsigned cl = (unsigned)info.x >> 30;
+    if (cl == CLS_PRUNE) return;
+    dst[(size_t)(info.x & 0x3fffffff) * w + col] = val;
+    if (cl == CLS_KEEP) return;
+    float nv = 0.f;
+    if (SET == 0) nv = new_row_value<A>(val, cl == CLS_SPLIT, (int64_t)row0 + r, info.y - K - C, col, S, z);
+    dst[(size_t)info.y * w + col] = nv;
+  };
+  if (rows_here == 32) {
+    constexpr int NV = 8 * w;            // float4 per group
+    constexpr int U = w >= 16 ? 4 : 2;   // float4 loads in flight per lane
+    const float4 *__restrict__ g4 = reinterpret_cast<const float4 *>(gsrc);
+#pragma unroll 1
+    for (int q0 = 0; q0 < NV; q0 += 32 * U) {
+      float4 v[U];
+      int r0[U], c0[U];
+      bool live[U];
+#pragma unroll
+      for (int u = 0; u < U; u++) {  // all loads are issued before any is consumed
+        const int q = q0 + 32 * u + lane;
+        live[u] = false;
+        r0[u] = (4 * q) / w, c0[u] = 4 * q - r0[u] * w;
+        if (q < NV) {
+          const int r_last = w >= 4 ? r0[u] + (c0[u] + 3 >= w) : (4 * q + 3) / w;
+          for (int rr = r0[u]; rr <= r_last; rr++) live[u] = live[u] || ((unsigned)tab[rr].x >> 30) != CLS_PRUNE;
+          if (live[u]) v[u] = __ldg(g4 + q);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        if (!live[u]) continue;
+        const float val[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+        int rr = r0[u], cc = c0[u];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          emit(rr, cc, tab[rr], val[j]);
+          if (++cc == w) cc = 0, ++rr;
+        }
+      }
+    }
+  } else {  // the last, partial group of the array
+    for (int e = lane; e < rows_here * w; e += 32) {
+      const int r = e / w;
+      const int2 info = tab[r];
+      if (((unsigned)info.x >> 30) != CLS_PRUNE) emit(r, e - r * w, info, gsrc[e]);
+    }
+  }
+}
+
+// blockIdx.y = one (array, set) pair, the three wide [*, 45] arrays first (they are 76 % of the
+// bytes and should not form the tail).  One out-of-line loop per pair keeps the register count
+// at the widest single pair (ptxas interleaves inlined pairs otherwise: 125 registers).
+template <int A, int SET>
+__device__ __noinline__ void rows_loop(int N, const uint8_t *__restrict__ cls, const Slot3 *__restrict__ slots, int K,
+                                       int C, const Sets &S, const float *__restrict__ z, int2 *tab) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int groups = (N + 31) / 32;
+  for (int g = blockIdx.x * DG_WARPS + wid; g < groups; g += gridDim.x * DG_WARPS) {
+    const int row0 = g * 32, row = row0 + lane;
+    uint8_t c = CLS_PRUNE;
+    Slot3 sl{0, 0, 0};
+    if (row < N) {
+      c = cls[row];
+      sl = slots[row];
+    }
+    // (class | survivor slot, new-row slot); slots < N < 2^30
+    tab[lane] = make_int2((int)((unsigned)c << 30) | sl.k, c == CLS_SPLIT ? K + C + sl.s : K + sl.c);
+    __syncwarp();
+    rows_job<A, SET>(row0, min(32, N - row0), tab, K, C, S, z, lane);
+    __syncwarp();  // the table is rewritten for the next group
+  }
+}
+
+__global__ void __launch_bounds__(32 * DG_WARPS) k_density_apply_rows(int N, const uint8_t *__restrict__ cls,
+                                                                       const Slot3 *__restrict__ slots, int K, int C,
+                                                                       const __grid_constant__ Sets S,
+                                                                       const float *__restrict__ z) {
+  __shared__ int2 tabs[DG_WARPS][32];
+  int2 *tab = tabs[threadIdx.x >> 5];
+#define GSB_JOB(y, a, s) \
+  case y: rows_loop<a, s>(N, cls, slots, K, C, S, z, tab); break;
+  switch (blockIdx.y) {
+    GSB_JOB(0, 2, 0) GSB_JOB(1, 2, 1) GSB_JOB(2, 2, 2) GSB_JOB(3, 0, 0) GSB_JOB(4, 0, 1) GSB_JOB(5, 0, 2)
+    GSB_JOB(6, 1, 0) GSB_JOB(7, 1, 1) GSB_JOB(8, 1, 2) GSB_JOB(9, 3, 0) GSB_JOB(10, 3, 1) GSB_JOB(11, 3, 2)
+    GSB_JOB(12, 4, 0) GSB_JOB(13, 4, 1) GSB_JOB(14, 4, 2) GSB_JOB(15, 5, 0) GSB_JOB(16, 5, 1) GSB_JOB(17, 5, 2)
+  }
+#undef GSB_JOB
+}
+
 // gsmodel.py:320-331
 __global__ void k_reset_alpha(int64_t N, float *__restrict__ alphas_raw, float *__restrict__ m,
                               float *__restrict__ v, float val) {
@@ -304,7 +558,8 @@ size_t density_workspace_bytes(int64_t N) {
   size_t tmp = 0;
   thrust::transform_iterator<ClsToSlot, const uint8_t *, Slot3> it(static_cast<const uint8_t *>(nullptr), ClsToSlot());
   cub::DeviceScan::ExclusiveScan(nullptr, tmp, it, (Slot3 *)nullptr, SlotAdd(), Slot3{0, 0, 0}, (int)(N > 0 ? N : 1));
-  return 256 + tmp;  // [three int64 totals, padded to 256 B][scan temp]
+  const size_t mine = (size_t)((N + SC_ROWS - 1) / SC_ROWS + 1) * 3 * sizeof(int32_t);
+  return 256 + (tmp > mine ? tmp : mine);  // [three int64 totals, padded to 256 B][per-CTA counts | CUB temp (A/B)]
 }
 
 int launch_density_accumulate(int64_t N, const float *dloss_dus, const uint8_t *mask, float *grad_accum,
@@ -323,6 +578,30 @@ int launch_density_plan(int64_t N, const float *alphas_raw, const float *scales_
                         int64_t *counts_host, cudaStream_t st) {
   counts_host[0] = counts_host[1] = counts_host[2] = 0;
   if (N == 0) return 0;
+  static const int scan_variant = [] {  // 1 = the three hand-written kernels (default), 0 = cub::DeviceScan (A/B)
+    const char *e = getenv("GSB_DENSITY_SCAN_VARIANT");
+    return e != nullptr ? atoi(e) : GSB_DENSITY_DEFAULT_VARIANT;
+  }();
+  if (scan_variant == 1) {
+    int64_t *totals = static_cast<int64_t *>(ws);
+    int32_t *block_counts = reinterpret_cast<int32_t *>(static_cast<char *>(ws) + 256);
+    const int nb = (int)((N + SC_ROWS - 1) / SC_ROWS);
+    {
+      ProfScope ps(K_DENSITY_CLASSIFY, st);
+      k_density_classify_count<<<nb, SC_THREADS, 0, st>>>(N, alphas_raw, scales_raw, grad_accum, cunt, alpha_raw_min,
+                                                         scale_raw_max, grad_min, scale_clone_max, cls, block_counts);
+      GSB_CUDA_TRY(cudaGetLastError());
+    }
+    {
+      ProfScope ps(K_DENSITY_SCAN, st);
+      k_density_scan_blocks<<<1, 1024, 0, st>>>(nb, block_counts, totals);
+      k_density_slots<<<nb, SC_THREADS, 0, st>>>(N, cls, block_counts, reinterpret_cast<Slot3 *>(slots));
+      GSB_CUDA_TRY(cudaGetLastError());
+    }
+    GSB_CUDA_TRY(cudaMemcpyAsync(counts_host, totals, 3 * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    GSB_CUDA_TRY(cudaStreamSynchronize(st));
+    return 0;
+  }
   {
     ProfScope ps(K_DENSITY_CLASSIFY, st);
     k_density_classify<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(N, alphas_raw, scales_raw, grad_accum, cunt,
@@ -360,6 +639,25 @@ int launch_density_apply(int64_t N, const uint8_t *cls, const int32_t *slots, in
     S.dv[a] = dst_v ? dst_v[a] : nullptr;
   }
   ProfScope ps(K_DENSITY_APPLY, st);
+  static const int variant = [] {  // 1 = row groups (default), 0 = one element per thread (A/B)
+    const char *e = getenv("GSB_DENSITY_VARIANT");
+    return e != nullptr ? atoi(e) : GSB_DENSITY_DEFAULT_VARIANT;
+  }();
+  bool aligned = true;  // float4 reads of the source spans
+  for (int a = 0; a < 6; a++)
+    aligned = aligned && ((reinterpret_cast<uintptr_t>(S.p[a]) | reinterpret_cast<uintptr_t>(S.m[a]) |
+                           reinterpret_cast<uintptr_t>(S.v[a])) & 15) == 0;
+  if (variant == 1 && aligned && N < 23000000) {
+    int dev = 0, sms = 148;
+    GSB_CUDA_TRY(cudaGetDevice(&dev));
+    GSB_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int64_t blocks = (N + 32 * DG_WARPS - 1) / (32 * DG_WARPS);
+    const int grid_x = (int)(blocks < (int64_t)sms * 8 ? blocks : (int64_t)sms * 8);
+    k_density_apply_rows<<<dim3(grid_x, 18), 32 * DG_WARPS, 0, st>>>((int)N, cls, reinterpret_cast<const Slot3 *>(slots), (int)K,
+                                                          (int)C, S, z);
+    GSB_CUDA_TRY(cudaGetLastError());
+    return 0;
+  }
   dim3 grid(stream_grid((N * 45 + 3) / 4, 256), 18);
   if (N < 23000000)
     k_density_apply<int32_t><<<grid, 256, 0, st>>>((int32_t)N, cls, reinterpret_cast<const Slot3 *>(slots), (int32_t)K,

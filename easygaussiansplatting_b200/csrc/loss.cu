@@ -9,8 +9,14 @@
 //                and the final loss scalar.
 // Algorithmic bytes: 24 (read img, gt) + 36 (write maps) + 36 + 24 (read) + 12 (write grad)
 // = 132 B per pixel (x3 channels already counted) -> HBM roofline.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "kernels.h"
+
+#ifndef GSB_LOSS_DEFAULT_VARIANT
+#define GSB_LOSS_DEFAULT_VARIANT 0
+#endif
 
 namespace gsb {
 
@@ -196,6 +202,265 @@ __global__ void __launch_bounds__(256) k_ssim_bwd(int W, int H, const float *__r
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// Row-streaming variant (default).  The tiled kernels above spend 70 % of their instructions on
+// staging (index arithmetic, shared-memory traffic for both passes); here one lane owns one
+// image COLUMN and walks down a strip of rows:
+//   * a row of img and gt goes through a 48-column per-warp shared-memory line (the warp's 32
+//     columns + 8 either side, so that with W % 4 == 0 the line is 12 aligned float4 per image:
+//     ONE 16-byte load per lane and row); 22 LDS feed the 11 horizontal taps;
+//   * the vertical pass never touches shared memory: the last 11 horizontally filtered rows
+//     live in registers (the row loop is unrolled by 11 so the ring is statically indexed).
+// ~250 instructions per (pixel, channel) instead of ~500, same IEEE operations in the same
+// order as the tiled kernels (bit-identical maps).  Warps are independent (one __syncwarp per
+// row, no block barrier); the next row's load is in flight while the current row is filtered.
+constexpr int SWARPS = 4;  // warps per CTA, side by side: 128 columns
+constexpr int SLINE = 48;  // columns x0-8 .. x0+39 of a warp whose first column is x0
+constexpr int SPAD = 8;
+
+__device__ __forceinline__ int ring_slot(int i, int k) { return (i + 1 + k) % 11; }
+
+// One row of NIMG images into the warp's lines.  VEC: lane l < 12*NIMG' loads chunk l % 12 of image
+// l / 12 (a second round covers NIMG = 3); otherwise every lane loads columns lane and lane + 32.
+template <int NIMG, bool VEC>
+struct RowFetch {
+  static constexpr int ROUNDS = VEC ? (12 * NIMG + 31) / 32 : 1;
+  const float *src[VEC ? ROUNDS : 2 * NIMG];  // per-lane source pointers at row 0 (column folded in)
+  float *dst[VEC ? ROUNDS : 2 * NIMG];        // per-lane destinations in line buffer 0
+  bool ok[VEC ? ROUNDS : 2 * NIMG];
+  float4 v4[VEC ? ROUNDS : 1];
+  float v1[VEC ? 1 : 2 * NIMG];
+
+  // img0..2: row 0 of the (up to three) planes; line: this warp's [NIMG][2][SLINE] buffers
+  __device__ __forceinline__ void init(int lane, int x0, int W, const float *img0, const float *img1,
+                                       const float *img2, float (*line)[2][SLINE]) {
+    if constexpr (VEC) {
+#pragma unroll
+      for (int r = 0; r < ROUNDS; r++) {
+        const int q = lane + 32 * r, im = q / 12, ch = q - 12 * im, col = x0 - SPAD + 4 * ch;
+        ok[r] = q < 12 * NIMG && col >= 0 && col < W;
+        const int imc = im < NIMG ? im : 0;
+        src[r] = (imc == 0 ? img0 : (imc == 1 ? img1 : img2)) + col;
+        dst[r] = &line[imc][0][4 * ch];
+      }
+    } else {
+#pragma unroll
+      for (int m = 0; m < NIMG; m++)
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+          const int j = lane + 32 * h, col = x0 - SPAD + j;
+          ok[2 * m + h] = j < SLINE && col >= 0 && col < W;
+          src[2 * m + h] = (m == 0 ? img0 : (m == 1 ? img1 : img2)) + col;
+          dst[2 * m + h] = &line[m][0][j < SLINE ? j : 0];
+        }
+    }
+  }
+  __device__ __forceinline__ void fetch(int yy, int W, int H) {
+    const bool yin = yy >= 0 && yy < H;
+    const int o = yy * W;
+    if constexpr (VEC) {
+#pragma unroll
+      for (int r = 0; r < ROUNDS; r++) {
+        v4[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (yin && ok[r]) v4[r] = __ldg(reinterpret_cast<const float4 *>(src[r] + o));
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < 2 * NIMG; e++) {
+        v1[e] = 0.f;
+        if (yin && ok[e]) v1[e] = __ldg(src[e] + o);
+      }
+    }
+  }
+  __device__ __forceinline__ void stage(int buf, int lane) {  // buf: 0 / 1
+    const int off = buf * SLINE;
+    if constexpr (VEC) {
+#pragma unroll
+      for (int r = 0; r < ROUNDS; r++)
+        if (lane + 32 * r < 12 * NIMG) *reinterpret_cast<float4 *>(dst[r] + off) = v4[r];
+    } else {
+#pragma unroll
+      for (int e = 0; e < 2 * NIMG; e++)
+        if ((e & 1) == 0 || lane + 32 < SLINE) dst[e][off] = v1[e];
+    }
+  }
+};
+
+template <bool VEC>
+__global__ void __launch_bounds__(32 * SWARPS, 4) k_ssim_fwd_rows(int W, int H, int SH, const float *__restrict__ img,
+                                                                  const float *__restrict__ gt, Win11 win,
+                                                                  float *__restrict__ maps,
+                                                                  double *__restrict__ acc) {
+  __shared__ __align__(16) float line[SWARPS][2][2][SLINE];  // [warp][img | gt][buffer][column]
+  __shared__ float red[2][SWARPS];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int x0 = (blockIdx.x * SWARPS + wid) * 32, x = x0 + lane;
+  const int yb = blockIdx.y * SH, ye = min(yb + SH, H), c = blockIdx.z;
+  const int HW = H * W;  // (the host keeps H * W < 2^31 / 9 for this variant)
+  float *__restrict__ mp0 = maps + (size_t)c * HW, *__restrict__ mp1 = mp0 + (size_t)3 * HW,
+                      *__restrict__ mp2 = mp0 + (size_t)6 * HW;
+  const bool xin = x < W;
+  const int n = ye - yb + 2 * LR;  // input rows yb-5 .. ye+4
+  float l1 = 0.f, ss = 0.f;
+  const float C1 = 0.01f * 0.01f, C2 = 0.03f * 0.03f;
+  if (x0 < W) {  // (whole warps beyond the right edge only take part in the final reduction)
+    RowFetch<2, VEC> rf;
+    rf.init(lane, x0, W, img + (size_t)c * HW, gt + (size_t)c * HW, nullptr, line[wid]);
+    float2 r01[11], r23[11];
+    float r4[11];
+    rf.fetch(yb - LR, W, H);
+    rf.stage(0, lane);
+    __syncwarp();
+    for (int t0 = 0; t0 < n; t0 += 11) {
+#pragma unroll
+      for (int i = 0; i < 11; i++) {
+        const int t = t0 + i;
+        if (t < n) {
+          const int yy = yb - LR + t;
+          rf.fetch(yy + 1, W, H);  // row t + 1 (beyond the strip's last input row: staged, never used)
+          const float *ra = &line[wid][0][t & 1][lane + SPAD - LR], *rb = &line[wid][1][t & 1][lane + SPAD - LR];
+          float2 mm = make_float2(0.f, 0.f), ee = make_float2(0.f, 0.f);
+          float e12 = 0.f;
+#pragma unroll
+          for (int k = 0; k < 11; k++) {
+            const float2 w2 = make_float2(win.w[k], win.w[k]), ab = make_float2(ra[k], rb[k]);
+            if (k == LR && t >= LR && t < n - LR) l1 += fabsf(ab.x - ab.y);  // the strip's own rows
+            mm = __ffma2_rn(w2, ab, mm);
+            const float2 wab = __fmul2_rn(w2, ab);
+            ee = __ffma2_rn(wab, ab, ee);
+            e12 = fmaf(wab.x, ab.y, e12);
+          }
+          r01[i] = mm, r23[i] = ee, r4[i] = e12;
+          if (t >= 2 * LR && xin) {  // output row yy - 5 = yb + t - 10: its 11 rows are in the ring
+            float2 v01 = make_float2(0.f, 0.f), v23 = make_float2(0.f, 0.f);
+            float v4 = 0.f;
+#pragma unroll
+            for (int k = 0; k < 11; k++) {
+              const float2 w2 = make_float2(win.w[k], win.w[k]);
+              v01 = __ffma2_rn(w2, r01[ring_slot(i, k)], v01);
+              v23 = __ffma2_rn(w2, r23[ring_slot(i, k)], v23);
+              v4 = fmaf(win.w[k], r4[ring_slot(i, k)], v4);
+            }
+            const float mu1 = v01.x, mu2 = v01.y;
+            const float s11 = v23.x - mu1 * mu1, s22 = v23.y - mu2 * mu2, s12 = v4 - mu1 * mu2;
+            const float A1 = 2.f * mu1 * mu2 + C1, A2 = 2.f * s12 + C2;
+            const float B1 = mu1 * mu1 + mu2 * mu2 + C1, B2 = s11 + s22 + C2;
+            const float inv = 1.0f / (B1 * B2);
+            const float ssim = A1 * A2 * inv;
+            ss += ssim;
+            const int o = (yy - LR) * W + x;
+            mp0[o] = (2.f * mu2 * (A2 - A1)) * inv - ssim * (2.f * mu1 * (B2 - B1)) * inv;  // dSSIM/dmu1
+            mp1[o] = -ssim / B2;                                                            // dSSIM/dE11
+            mp2[o] = 2.f * A1 * inv;                                                        // dSSIM/dE12
+          }
+          rf.stage((t + 1) & 1, lane);
+          __syncwarp();
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    l1 += __shfl_xor_sync(0xffffffffu, l1, o);
+    ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  }
+  if (lane == 0) { red[0][wid] = l1; red[1][wid] = ss; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+    for (int w = 0; w < SWARPS; w++) { a0 += (double)red[0][w]; a1 += (double)red[1][w]; }
+    atomicAdd(acc + 0, a0);
+    atomicAdd(acc + 1, a1);
+  }
+}
+
+template <bool VEC>
+__global__ void __launch_bounds__(32 * SWARPS, 4) k_ssim_bwd_rows(int W, int H, int SH, const float *__restrict__ img,
+                                                                  const float *__restrict__ gt, Win11 win,
+                                                                  const float *__restrict__ maps,
+                                                                  const double *__restrict__ acc, float lambda,
+                                                                  float *__restrict__ loss_out,
+                                                                  float *__restrict__ grad) {
+  __shared__ __align__(16) float line[SWARPS][3][2][SLINE];  // [warp][map][buffer][column]
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int x0 = (blockIdx.x * SWARPS + wid) * 32, x = x0 + lane;
+  const int yb = blockIdx.y * SH, ye = min(yb + SH, H), c = blockIdx.z;
+  const int HW = H * W;
+  const double npix = 3.0 * (double)HW;
+  if (blockIdx.x == 0 && blockIdx.y == 0 && c == 0 && threadIdx.x == 0)
+    *loss_out = (float)((1.0 - (double)lambda) * (acc[0] / npix) + (double)lambda * (1.0 - acc[1] / npix));
+  if (grad == nullptr || x0 >= W) return;
+  const float *__restrict__ a = img + (size_t)c * HW, *__restrict__ b = gt + (size_t)c * HW;
+  float *__restrict__ gr = grad + (size_t)c * HW;
+  // (the maps are zero outside the image: conv2d's zero padding, transposed)
+  RowFetch<3, VEC> rf;
+  rf.init(lane, x0, W, maps + (size_t)c * HW, maps + (size_t)(3 + c) * HW, maps + (size_t)(6 + c) * HW, line[wid]);
+  const bool xin = x < W;
+  const int n = ye - yb + 2 * LR;
+  const float inv_n = (float)(1.0 / npix);
+  float2 r01[11];
+  float r2[11];
+  rf.fetch(yb - LR, W, H);
+  rf.stage(0, lane);
+  __syncwarp();
+  for (int t0 = 0; t0 < n; t0 += 11) {
+#pragma unroll
+    for (int i = 0; i < 11; i++) {
+      const int t = t0 + i;
+      if (t < n) {
+        const int yy = yb - LR + t;
+        rf.fetch(yy + 1, W, H);
+        const bool emit = t >= 2 * LR && xin;
+        const int o = (yy - LR) * W + x;
+        float p = 0.f, g = 0.f;
+        if (emit) p = __ldg(a + o), g = __ldg(b + o);  // in flight while the row is filtered
+        const float *q0 = &line[wid][0][t & 1][lane + SPAD - LR], *q1 = &line[wid][1][t & 1][lane + SPAD - LR],
+                    *q2 = &line[wid][2][t & 1][lane + SPAD - LR];
+        float2 h01 = make_float2(0.f, 0.f);
+        float h2 = 0.f;
+#pragma unroll
+        for (int k = 0; k < 11; k++) {
+          h01 = __ffma2_rn(make_float2(win.w[k], win.w[k]), make_float2(q0[k], q1[k]), h01);
+          h2 = fmaf(win.w[k], q2[k], h2);
+        }
+        r01[i] = h01, r2[i] = h2;
+        if (emit) {
+          float2 v01 = make_float2(0.f, 0.f);
+          float v2 = 0.f;
+#pragma unroll
+          for (int k = 0; k < 11; k++) {
+            v01 = __ffma2_rn(make_float2(win.w[k], win.w[k]), r01[ring_slot(i, k)], v01);
+            v2 = fmaf(win.w[k], r2[ring_slot(i, k)], v2);
+          }
+          const float sgn = (p > g) ? 1.f : ((p < g) ? -1.f : 0.f);
+          gr[o] = (1.f - lambda) * sgn * inv_n - lambda * inv_n * (v01.x + 2.f * p * v01.y + g * v2);
+        }
+        rf.stage((t + 1) & 1, lane);
+        __syncwarp();
+      }
+    }
+  }
+}
+
+// rows per strip: about one resident wave of warps (a strip pays 10 halo rows, so the longer the
+// better, but every SM needs its share); GSB_LOSS_STRIP overrides (A/B)
+static int strip_rows(int H, int W) {
+  static const int forced = [] {
+    const char *e = getenv("GSB_LOSS_STRIP");
+    return e != nullptr ? atoi(e) : 0;
+  }();
+  if (forced > 0) return forced;
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int xblocks = (W + 32 * SWARPS - 1) / (32 * SWARPS);
+  const int ctas_wanted = sms * 4;  // 4 CTAs of 4 warps per SM at ~110 registers
+  int strips = ctas_wanted / (3 * xblocks);
+  if (strips < 1) strips = 1;
+  int sh = (H + strips - 1) / strips;
+  return sh < 16 ? 16 : sh;
+}
+
 size_t gau_loss_workspace_bytes(int H, int W) {
   return 256 + (size_t)9 * H * W * sizeof(float);  // [2 doubles, padded] [3 maps x 3 channels]
 }
@@ -215,6 +480,34 @@ int launch_gau_loss(int H, int W, const float *img, const float *gt, float lambd
   double *acc = static_cast<double *>(ws);
   float *maps = reinterpret_cast<float *>(static_cast<char *>(ws) + 256);
   GSB_CUDA_TRY(cudaMemsetAsync(acc, 0, 2 * sizeof(double), st));
+  static const int variant = [] {  // 1 = row streaming (default), 0 = the tiled kernels (A/B)
+    const char *e = getenv("GSB_LOSS_VARIANT");
+    return e != nullptr ? atoi(e) : GSB_LOSS_DEFAULT_VARIANT;
+  }();
+  if (variant == 1 && (long long)H * W < (1ll << 31) / 9) {  // (int element offsets inside the kernels)
+    const int SH = strip_rows(H, W);
+    const dim3 grid((W + 32 * SWARPS - 1) / (32 * SWARPS), (H + SH - 1) / SH, 3);
+    // 16-byte row loads need every row (and plane) of all five arrays 16-byte aligned
+    const bool vec = W % 4 == 0 && ((reinterpret_cast<uintptr_t>(img) | reinterpret_cast<uintptr_t>(gt) |
+                                     reinterpret_cast<uintptr_t>(maps)) & 15) == 0;
+    {
+      ProfScope ps(K_LOSS_FWD, st);
+      if (vec)
+        k_ssim_fwd_rows<true><<<grid, 32 * SWARPS, 0, st>>>(W, H, SH, img, gt, win, maps, acc);
+      else
+        k_ssim_fwd_rows<false><<<grid, 32 * SWARPS, 0, st>>>(W, H, SH, img, gt, win, maps, acc);
+    }
+    GSB_CUDA_TRY(cudaGetLastError());
+    {
+      ProfScope ps(K_LOSS_BWD, st);
+      if (vec)
+        k_ssim_bwd_rows<true><<<grid, 32 * SWARPS, 0, st>>>(W, H, SH, img, gt, win, maps, acc, lambda, loss_out, grad);
+      else
+        k_ssim_bwd_rows<false><<<grid, 32 * SWARPS, 0, st>>>(W, H, SH, img, gt, win, maps, acc, lambda, loss_out, grad);
+    }
+    GSB_CUDA_TRY(cudaGetLastError());
+    return 0;
+  }
   const dim3 grid((W + LW - 1) / LW, (H + LH - 1) / LH, 3);
   {
     ProfScope ps(K_LOSS_FWD, st);

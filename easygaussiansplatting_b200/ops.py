@@ -266,9 +266,14 @@ def splat(height, width, us, cinv2ds, alphas, depths, colors, areas, records=Non
 
 
 # The forward leaves the packed per-Gaussian records in its workspace (or got them from
-# `preprocess`); splatB can reuse them instead of packing the same records again, provided it is called with the very tensors the
-# forward saw, unmodified (checked through data_ptr + torch's in-place version counter).
-_RECORD_CACHE = []  # [(gsid_ptr, P, ws, offset, ((ptr, version), ...))], newest first, <= 2 entries
+# `preprocess`); splatB can reuse them instead of packing the same records again.  The handle
+# travels ON the gsid_per_patch tensor `splat` returns (an attribute of that tensor object; it
+# survives autograd's save_for_backward), so identity is never inferred from addresses the
+# caching allocator may hand out again, and the workspace lives exactly as long as that tensor.
+# The inputs must still be the very tensors the forward saw, unmodified (data_ptr + torch's
+# in-place version counter); writes that bypass the counter (`.data`, foreign kernels) are the
+# caller's to announce with `forget_records(gsid)`.
+_RECORDS_ATTR = "_gsb_records"
 
 
 def _input_key(inputs):
@@ -280,25 +285,29 @@ def _input_key(inputs):
 
 def _remember_records(gsid, ws, offset, inputs):
     key = _input_key(inputs)
-    if key is None:
-        return
-    _RECORD_CACHE.insert(0, (gsid.data_ptr(), gsid.numel(), ws, offset, key))
-    del _RECORD_CACHE[2:]
+    if key is not None:
+        setattr(gsid, _RECORDS_ATTR, (ws, offset, key, gsid.data_ptr(), gsid.numel()))
 
 
 def _cached_records(gsid, inputs):
-    key = _input_key(inputs)
-    if key is None:
+    h = getattr(gsid, _RECORDS_ATTR, None)
+    if h is None:
         return None
-    for gptr, P, ws, offset, k in _RECORD_CACHE:
-        if gptr == gsid.data_ptr() and P == gsid.numel() and k == key:
-            return ws.data_ptr() + offset
-    return None
+    ws, offset, key, gptr, P = h
+    if gptr != gsid.data_ptr() or P != gsid.numel() or key != _input_key(inputs):
+        return None
+    return ws.data_ptr() + offset
+
+
+def forget_records(gsid):
+    """Drop the packed records `splat` attached to its gsid_per_patch output (frees the forward
+    workspace early; splatB then packs the records again)."""
+    if hasattr(gsid, _RECORDS_ATTR):
+        delattr(gsid, _RECORDS_ATTR)
 
 
 def clear_record_cache():
-    """Drop the (at most two) forward workspaces kept alive for splatB's benefit."""
-    del _RECORD_CACHE[:]
+    """Kept for callers of the round-1 API: there is no global cache any more (see above)."""
 
 
 def splatB(height, width, us, cinv2ds, alphas, depths, colors, contrib, final_tau,

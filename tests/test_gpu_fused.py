@@ -158,7 +158,11 @@ def test_record_cache_and_key_widths():
     out = g.splat(H, W, us, ci, al, d, col, ar)
     assert ops._cached_records(out[4], (us, ci, al, col)) is not None
     g1 = g.splatB(H, W, us, ci, al, d, col, out[1], out[2], out[3], out[4], dl)      # cached records
-    ops.clear_record_cache()
+    # the handle rides on the tensor object: a copy (or any other tensor that happens to get the
+    # same address later) has none
+    assert ops._cached_records(out[4].clone(), (us, ci, al, col)) is None
+    ops.forget_records(out[4])
+    assert ops._cached_records(out[4], (us, ci, al, col)) is None
     g2 = g.splatB(H, W, us, ci, al, d, col, out[1], out[2], out[3], out[4], dl)      # re-packed
     for a, b in zip(g1, g2):
         assert torch.allclose(a, b, rtol=1e-4, atol=1e-6 * a.abs().max().item())
@@ -204,7 +208,6 @@ def test_fused_shortcuts_match_separate_passes():
         assert torch.equal(a, b)
     us, ci, col, d, ar = plain
     s1 = ops.splat(H, W, us, ci, al, d.clone(), col, ar.clone())
-    ops.clear_record_cache()
     s2 = ops.splat(H, W, us, ci, al, d.clone(), col, ar.clone(), records=withrec[5])
     for a, b in zip(s1, s2):
         assert torch.equal(a, b)
