@@ -26,7 +26,7 @@
 #include "kernels.h"
 
 #ifndef GSB_DENSITY_DEFAULT_VARIANT
-#define GSB_DENSITY_DEFAULT_VARIANT 0
+#define GSB_DENSITY_DEFAULT_VARIANT 1
 #endif
 
 namespace gsb {
@@ -99,19 +99,19 @@ __global__ void k_density_classify(int64_t N, const float *__restrict__ alphas_r
 }
 
 // ---- the slots (exclusive scan of the three class counters in row order), hand-written:
-//   k_density_classify_count  classify 2048 rows per CTA and leave the CTA's three counts;
+//   k_density_classify_count  classify 1024 rows per CTA and leave the CTA's three counts;
 //   k_density_scan_blocks     one CTA turns the per-CTA counts into exclusive offsets + totals;
-//   k_density_slots           every CTA re-reads its 2048 class bytes (8 consecutive rows per
+//   k_density_slots           every CTA re-reads its 1024 class bytes (4 consecutive rows per
 //                             thread), scans them locally and writes the 12-byte slots.
 // 25 B per Gaussian in total; the three launches replace cub::DeviceScan over a 12-byte struct.
-constexpr int SC_THREADS = 256, SC_PER = 8, SC_ROWS = SC_THREADS * SC_PER;
+constexpr int SC_THREADS = 256, SC_PER = 4, SC_ROWS = SC_THREADS * SC_PER;
 
 __global__ void __launch_bounds__(SC_THREADS) k_density_classify_count(
     int64_t N, const float *__restrict__ alphas_raw, const float *__restrict__ scales_raw,
     const float *__restrict__ acc, const int32_t *__restrict__ cnt, float alpha_raw_min, float scale_raw_max,
     float grad_min, float scale_clone_max, uint8_t *__restrict__ cls, int32_t *__restrict__ block_counts) {
   __shared__ uint32_t red[2][SC_THREADS / 32];
-  uint32_t kc = 0, sp = 0;  // (survivors | clones << 16), splits: at most 2048 each per CTA
+  uint32_t kc = 0, sp = 0;  // (survivors | clones << 16), splits: at most SC_ROWS each per CTA
 #pragma unroll
   for (int j = 0; j < SC_PER; j++) {
     const int64_t i = (int64_t)blockIdx.x * SC_ROWS + j * SC_THREADS + threadIdx.x;
@@ -329,10 +329,12 @@ __global__ void __launch_bounds__(256) k_density_apply(I N, const uint8_t *__res
 // ---- row-group variant (default for N < 23 M): a warp moves 32 consecutive Gaussians of one array.
 // The per-Gaussian plan (class, survivor slot, new-row slot) is read once per group into a
 // 32-entry shared-memory table instead of once per element (13 B per 4-byte element in the
-// kernel above); the group's source span of every array is 128 w bytes, 16-byte aligned, so
-// it is read with float4 loads, two in flight per lane; one division per float4.  Spans that
-// belong to pruned Gaussians only are not loaded.  Stores stay 4-byte (destination rows of a
-// compacted [*, 45] or [*, 3] array are only 4-byte aligned).
+// kernel above).  Loads and stores are 4-byte but fully coalesced: lane l handles elements
+// l, l + 32, ... of the group's contiguous source span, 8 loads in flight per lane for the wide
+// arrays; consecutive survivors are consecutive in the destination too, so a store instruction
+// writes whole 32-byte sectors.  (A first version read the span with float4 loads and wrote the
+// four components with stride-16-byte stores: quarter-filled sectors, 0.57 ms against the 0.45 ms
+// of the kernel above.)  Elements of pruned Gaussians are not loaded.
 constexpr int DG_WARPS = 8;
 
 // the value a clone / split writes at its new row (parameters; Adam moments start at 0)
@@ -372,50 +374,28 @@ __device__ __forceinline__ void rows_job(int row0, int rows_here, const int2 *__
     if (SET == 0) nv = new_row_value<A>(val, cl == CLS_SPLIT, (int64_t)row0 + r, info.y - K - C, col, S, z);
     dst[(size_t)info.y * w + col] = nv;
   };
-  if (rows_here == 32) {
-    constexpr int NV = 8 * w;            // float4 per group
-    constexpr int U = w >= 16 ? 4 : 2;   // float4 loads in flight per lane
-    const float4 *__restrict__ g4 = reinterpret_cast<const float4 *>(gsrc);
+  constexpr int U = w >= 16 ? 8 : (w >= 3 ? 3 : 1);  // loads in flight per lane (w = 3: 96 elements = 3 rounds)
+  const int nelem = rows_here * w;
 #pragma unroll 1
-    for (int q0 = 0; q0 < NV; q0 += 32 * U) {
-      float4 v[U];
-      int r0[U], c0[U];
-      bool live[U];
+  for (int e0 = 0; e0 < nelem; e0 += 32 * U) {
+    float v[U];
+    int2 info[U];
+    int r[U];
 #pragma unroll
-      for (int u = 0; u < U; u++) {  // all loads are issued before any is consumed
-        const int q = q0 + 32 * u + lane;
-        live[u] = false;
-        r0[u] = (4 * q) / w, c0[u] = 4 * q - r0[u] * w;
-        if (q < NV) {
-          const int r_last = w >= 4 ? r0[u] + (c0[u] + 3 >= w) : (4 * q + 3) / w;
-          for (int rr = r0[u]; rr <= r_last; rr++) live[u] = live[u] || ((unsigned)tab[rr].x >> 30) != CLS_PRUNE;
-          if (live[u]) v[u] = __ldg(g4 + q);
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < U; u++) {
-        if (!live[u]) continue;
-        const float val[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
-        int rr = r0[u], cc = c0[u];
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-          emit(rr, cc, tab[rr], val[j]);
-          if (++cc == w) cc = 0, ++rr;
-        }
+    for (int u = 0; u < U; u++) {  // all loads are issued before any is consumed
+      const int e = e0 + 32 * u + lane;
+      info[u] = make_int2((int)((unsigned)CLS_PRUNE << 30), 0);
+      r[u] = e / w;
+      if (e < nelem) {
+        info[u] = tab[r[u]];
+        if (((unsigned)info[u].x >> 30) != CLS_PRUNE) v[u] = __ldg(gsrc + e);
       }
     }
-  } else {  // the last, partial group of the array
-    for (int e = lane; e < rows_here * w; e += 32) {
-      const int r = e / w;
-      const int2 info = tab[r];
-      if (((unsigned)info.x >> 30) != CLS_PRUNE) emit(r, e - r * w, info, gsrc[e]);
-    }
+#pragma unroll
+    for (int u = 0; u < U; u++) emit(r[u], e0 + 32 * u + lane - r[u] * w, info[u], v[u]);
   }
 }
 
-// blockIdx.y = one (array, set) pair, the three wide [*, 45] arrays first (they are 76 % of the
-// bytes and should not form the tail).  One out-of-line loop per pair keeps the register count
-// at the widest single pair (ptxas interleaves inlined pairs otherwise: 125 registers).
 template <int A, int SET>
 __device__ __noinline__ void rows_loop(int N, const uint8_t *__restrict__ cls, const Slot3 *__restrict__ slots, int K,
                                        int C, const Sets &S, const float *__restrict__ z, int2 *tab) {
@@ -643,11 +623,7 @@ int launch_density_apply(int64_t N, const uint8_t *cls, const int32_t *slots, in
     const char *e = getenv("GSB_DENSITY_VARIANT");
     return e != nullptr ? atoi(e) : GSB_DENSITY_DEFAULT_VARIANT;
   }();
-  bool aligned = true;  // float4 reads of the source spans
-  for (int a = 0; a < 6; a++)
-    aligned = aligned && ((reinterpret_cast<uintptr_t>(S.p[a]) | reinterpret_cast<uintptr_t>(S.m[a]) |
-                           reinterpret_cast<uintptr_t>(S.v[a])) & 15) == 0;
-  if (variant == 1 && aligned && N < 23000000) {
+  if (variant == 1 && N < 23000000) {
     int dev = 0, sms = 148;
     GSB_CUDA_TRY(cudaGetDevice(&dev));
     GSB_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));

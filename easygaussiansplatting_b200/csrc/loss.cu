@@ -15,7 +15,13 @@
 #include "kernels.h"
 
 #ifndef GSB_LOSS_DEFAULT_VARIANT
-#define GSB_LOSS_DEFAULT_VARIANT 0
+#define GSB_LOSS_DEFAULT_VARIANT 1
+#endif
+#ifndef GSB_LOSS_FWD_MINB  // resident CTAs (of 4 warps) the row kernels are compiled for
+#define GSB_LOSS_FWD_MINB 4
+#endif
+#ifndef GSB_LOSS_BWD_MINB
+#define GSB_LOSS_BWD_MINB 4
 #endif
 
 namespace gsb {
@@ -210,7 +216,7 @@ __global__ void __launch_bounds__(256) k_ssim_bwd(int W, int H, const float *__r
 //     columns + 8 either side, so that with W % 4 == 0 the line is 12 aligned float4 per image:
 //     ONE 16-byte load per lane and row); 22 LDS feed the 11 horizontal taps;
 //   * the vertical pass never touches shared memory: the last 11 horizontally filtered rows
-//     live in registers (the row loop is unrolled by 11 so the ring is statically indexed).
+//     live in registers (the row loop is unrolled so that the ring is statically indexed).
 // ~250 instructions per (pixel, channel) instead of ~500, same IEEE operations in the same
 // order as the tiled kernels (bit-identical maps).  Warps are independent (one __syncwarp per
 // row, no block barrier); the next row's load is in flight while the current row is filtered.
@@ -218,7 +224,11 @@ constexpr int SWARPS = 4;  // warps per CTA, side by side: 128 columns
 constexpr int SLINE = 48;  // columns x0-8 .. x0+39 of a warp whose first column is x0
 constexpr int SPAD = 8;
 
-__device__ __forceinline__ int ring_slot(int i, int k) { return (i + 1 + k) % 11; }
+// The ring of horizontally filtered rows has 12 slots (11 live): the row loop is unrolled by 12,
+// an EVEN count, so that besides the ring slots the parity of the row (line buffer, register
+// set of the rows in flight) is static in every unrolled copy.
+constexpr int RING = 12;
+__device__ __forceinline__ int ring_slot(int i, int k) { return (i + 2 + k) % RING; }  // row t - 10 + k, t % 12 == i
 
 // One row of NIMG images into the warp's lines.  VEC: lane l < 12*NIMG' loads chunk l % 12 of image
 // l / 12 (a second round covers NIMG = 3); otherwise every lane loads columns lane and lane + 32.
@@ -228,8 +238,10 @@ struct RowFetch {
   const float *src[VEC ? ROUNDS : 2 * NIMG];  // per-lane source pointers at row 0 (column folded in)
   float *dst[VEC ? ROUNDS : 2 * NIMG];        // per-lane destinations in line buffer 0
   bool ok[VEC ? ROUNDS : 2 * NIMG];
-  float4 v4[VEC ? ROUNDS : 1];
-  float v1[VEC ? 1 : 2 * NIMG];
+  struct Row {  // one row in flight
+    float4 v4[VEC ? ROUNDS : 1];
+    float v1[VEC ? 1 : 2 * NIMG];
+  };
 
   // img0..2: row 0 of the (up to three) planes; line: this warp's [NIMG][2][SLINE] buffers
   __device__ __forceinline__ void init(int lane, int x0, int W, const float *img0, const float *img1,
@@ -255,39 +267,41 @@ struct RowFetch {
         }
     }
   }
-  __device__ __forceinline__ void fetch(int yy, int W, int H) {
+  __device__ __forceinline__ Row fetch(int yy, int W, int H) const {
+    Row row;
     const bool yin = yy >= 0 && yy < H;
     const int o = yy * W;
     if constexpr (VEC) {
 #pragma unroll
       for (int r = 0; r < ROUNDS; r++) {
-        v4[r] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (yin && ok[r]) v4[r] = __ldg(reinterpret_cast<const float4 *>(src[r] + o));
+        row.v4[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (yin && ok[r]) row.v4[r] = __ldg(reinterpret_cast<const float4 *>(src[r] + o));
       }
     } else {
 #pragma unroll
       for (int e = 0; e < 2 * NIMG; e++) {
-        v1[e] = 0.f;
-        if (yin && ok[e]) v1[e] = __ldg(src[e] + o);
+        row.v1[e] = 0.f;
+        if (yin && ok[e]) row.v1[e] = __ldg(src[e] + o);
       }
     }
+    return row;
   }
-  __device__ __forceinline__ void stage(int buf, int lane) {  // buf: 0 / 1
+  __device__ __forceinline__ void stage(int buf, int lane, const Row &row) const {  // buf: 0 / 1
     const int off = buf * SLINE;
     if constexpr (VEC) {
 #pragma unroll
       for (int r = 0; r < ROUNDS; r++)
-        if (lane + 32 * r < 12 * NIMG) *reinterpret_cast<float4 *>(dst[r] + off) = v4[r];
+        if (lane + 32 * r < 12 * NIMG) *reinterpret_cast<float4 *>(dst[r] + off) = row.v4[r];
     } else {
 #pragma unroll
       for (int e = 0; e < 2 * NIMG; e++)
-        if ((e & 1) == 0 || lane + 32 < SLINE) dst[e][off] = v1[e];
+        if ((e & 1) == 0 || lane + 32 < SLINE) dst[e][off] = row.v1[e];
     }
   }
 };
 
 template <bool VEC>
-__global__ void __launch_bounds__(32 * SWARPS, 4) k_ssim_fwd_rows(int W, int H, int SH, const float *__restrict__ img,
+__global__ void __launch_bounds__(32 * SWARPS, GSB_LOSS_FWD_MINB) k_ssim_fwd_rows(int W, int H, int SH, const float *__restrict__ img,
                                                                   const float *__restrict__ gt, Win11 win,
                                                                   float *__restrict__ maps,
                                                                   double *__restrict__ acc) {
@@ -306,19 +320,27 @@ __global__ void __launch_bounds__(32 * SWARPS, 4) k_ssim_fwd_rows(int W, int H, 
   if (x0 < W) {  // (whole warps beyond the right edge only take part in the final reduction)
     RowFetch<2, VEC> rf;
     rf.init(lane, x0, W, img + (size_t)c * HW, gt + (size_t)c * HW, nullptr, line[wid]);
-    float2 r01[11], r23[11];
-    float r4[11];
-    rf.fetch(yb - LR, W, H);
-    rf.stage(0, lane);
+    float2 r01[RING], r23[RING];
+    float r4[RING];
+    // Software pipeline over rows: row t is filtered out of line buffer t & 1 while row t + 1
+    // (loaded two iterations ago) is stored into the other buffer and the load of row t + 3 is
+    // issued into the register set that just emptied: two rows are in flight per lane, a load
+    // has ~1.7 iterations (~400 instructions) to arrive.  (One row ahead left 60-110 instructions: 68 % of the backward kernel's warp
+    // time was spent waiting for it, profiles/r2_ncu_loss_density_summary.txt.)
+    rf.stage(0, lane, rf.fetch(yb - LR, W, H));
     __syncwarp();
-    for (int t0 = 0; t0 < n; t0 += 11) {
+    typename RowFetch<2, VEC>::Row rows[2];  // row r in flight lives in rows[r & 1]
+    rows[1] = rf.fetch(yb - LR + 1, W, H);
+    rows[0] = rf.fetch(yb - LR + 2, W, H);
+    for (int t0 = 0; t0 < n; t0 += RING) {
 #pragma unroll
-      for (int i = 0; i < 11; i++) {
+      for (int i = 0; i < RING; i++) {
         const int t = t0 + i;
         if (t < n) {
           const int yy = yb - LR + t;
-          rf.fetch(yy + 1, W, H);  // row t + 1 (beyond the strip's last input row: staged, never used)
-          const float *ra = &line[wid][0][t & 1][lane + SPAD - LR], *rb = &line[wid][1][t & 1][lane + SPAD - LR];
+          rf.stage((i + 1) & 1, lane, rows[(i + 1) & 1]);  // row t + 1 (past the strip's last input row: never used)
+          rows[(i + 1) & 1] = rf.fetch(yy + 3, W, H);
+          const float *ra = &line[wid][0][i & 1][lane + SPAD - LR], *rb = &line[wid][1][i & 1][lane + SPAD - LR];
           float2 mm = make_float2(0.f, 0.f), ee = make_float2(0.f, 0.f);
           float e12 = 0.f;
 #pragma unroll
@@ -353,7 +375,6 @@ __global__ void __launch_bounds__(32 * SWARPS, 4) k_ssim_fwd_rows(int W, int H, 
             mp1[o] = -ssim / B2;                                                            // dSSIM/dE11
             mp2[o] = 2.f * A1 * inv;                                                        // dSSIM/dE12
           }
-          rf.stage((t + 1) & 1, lane);
           __syncwarp();
         }
       }
@@ -376,7 +397,7 @@ __global__ void __launch_bounds__(32 * SWARPS, 4) k_ssim_fwd_rows(int W, int H, 
 }
 
 template <bool VEC>
-__global__ void __launch_bounds__(32 * SWARPS, 4) k_ssim_bwd_rows(int W, int H, int SH, const float *__restrict__ img,
+__global__ void __launch_bounds__(32 * SWARPS, GSB_LOSS_BWD_MINB) k_ssim_bwd_rows(int W, int H, int SH, const float *__restrict__ img,
                                                                   const float *__restrict__ gt, Win11 win,
                                                                   const float *__restrict__ maps,
                                                                   const double *__restrict__ acc, float lambda,
@@ -399,24 +420,28 @@ __global__ void __launch_bounds__(32 * SWARPS, 4) k_ssim_bwd_rows(int W, int H, 
   const bool xin = x < W;
   const int n = ye - yb + 2 * LR;
   const float inv_n = (float)(1.0 / npix);
-  float2 r01[11];
-  float r2[11];
-  rf.fetch(yb - LR, W, H);
-  rf.stage(0, lane);
+  float2 r01[RING];
+  float r2[RING];
+  rf.stage(0, lane, rf.fetch(yb - LR, W, H));  // (software pipeline over rows: see k_ssim_fwd_rows)
   __syncwarp();
-  for (int t0 = 0; t0 < n; t0 += 11) {
+  typename RowFetch<3, VEC>::Row rows[2];
+  rows[1] = rf.fetch(yb - LR + 1, W, H);
+  rows[0] = rf.fetch(yb - LR + 2, W, H);
+  float pq[2] = {0.f, 0.f}, gq[2] = {0.f, 0.f};  // img / gt of the output pixel of iteration t in [t & 1]
+  for (int t0 = 0; t0 < n; t0 += RING) {
 #pragma unroll
-    for (int i = 0; i < 11; i++) {
+    for (int i = 0; i < RING; i++) {
       const int t = t0 + i;
       if (t < n) {
         const int yy = yb - LR + t;
-        rf.fetch(yy + 1, W, H);
+        rf.stage((i + 1) & 1, lane, rows[(i + 1) & 1]);
+        rows[(i + 1) & 1] = rf.fetch(yy + 3, W, H);
         const bool emit = t >= 2 * LR && xin;
         const int o = (yy - LR) * W + x;
-        float p = 0.f, g = 0.f;
-        if (emit) p = __ldg(a + o), g = __ldg(b + o);  // in flight while the row is filtered
-        const float *q0 = &line[wid][0][t & 1][lane + SPAD - LR], *q1 = &line[wid][1][t & 1][lane + SPAD - LR],
-                    *q2 = &line[wid][2][t & 1][lane + SPAD - LR];
+        const float p = pq[i & 1], g = gq[i & 1];
+        if (t + 2 >= 2 * LR && t + 2 < n && xin) pq[i & 1] = __ldg(a + o + 2 * W), gq[i & 1] = __ldg(b + o + 2 * W);
+        const float *q0 = &line[wid][0][i & 1][lane + SPAD - LR], *q1 = &line[wid][1][i & 1][lane + SPAD - LR],
+                    *q2 = &line[wid][2][i & 1][lane + SPAD - LR];
         float2 h01 = make_float2(0.f, 0.f);
         float h2 = 0.f;
 #pragma unroll
@@ -436,7 +461,6 @@ __global__ void __launch_bounds__(32 * SWARPS, 4) k_ssim_bwd_rows(int W, int H, 
           const float sgn = (p > g) ? 1.f : ((p < g) ? -1.f : 0.f);
           gr[o] = (1.f - lambda) * sgn * inv_n - lambda * inv_n * (v01.x + 2.f * p * v01.y + g * v2);
         }
-        rf.stage((t + 1) & 1, lane);
         __syncwarp();
       }
     }
