@@ -8,18 +8,15 @@
 //
 // The reference rebuilds all 18 tensors (6 parameters + exp_avg + exp_avg_sq) with boolean
 // indexing and torch.cat, one tensor at a time, plus ~20 temporaries.  Here it is three
-// streaming passes: classify (one byte per Gaussian), one CUB scan over a three-counter
-// struct (the output slot of every survivor / clone / split), and one apply kernel that moves
-// every surviving row once and writes the new rows at the tail.  All of it is HBM-bound:
+// streaming passes: classify (one byte per Gaussian) + per-CTA counts, a two-kernel exclusive
+// scan of the three class counters (the output slot of every survivor / clone / split), and one
+// apply kernel that moves every surviving row once and writes the new rows at the tail.  All of it is HBM-bound:
 // algorithmic bytes = 24 N (classify + scan) + 2 * 708 * K + 708 * (C + S) for the full state
 // (59 floats x 3 sets = 708 B per Gaussian).
 //
 // Transcendentals are the accurate expf / logf / sqrtf / IEEE division (no fast-math here):
 // torch's CUDA kernels use the same libdevice routines, which keeps the clone / split values
 // within an ulp of the reference's.
-#include <cub/device/device_scan.cuh>
-#include <thrust/iterator/transform_iterator.h>
-
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -39,17 +36,6 @@ enum : uint8_t { CLS_KEEP = 0, CLS_CLONE = 1, CLS_SPLIT = 2, CLS_PRUNE = 3 };
 struct Slot3 {  // exclusive counts of survivors / clones / splits before this Gaussian
   int k, c, s;
 };
-struct SlotAdd {
-  __host__ __device__ Slot3 operator()(const Slot3 &a, const Slot3 &b) const {
-    return Slot3{a.k + b.k, a.c + b.c, a.s + b.s};
-  }
-};
-struct ClsToSlot {
-  __host__ __device__ Slot3 operator()(uint8_t c) const {
-    return Slot3{c != CLS_PRUNE, c == CLS_CLONE, c == CLS_SPLIT};
-  }
-};
-
 // gsmodel.py:219-234.  init != 0 is the first call after a density update: the norm of every
 // Gaussian is stored and the counter starts from the mask (:228-229).
 __global__ void k_density_accumulate(int64_t N, const float2 *__restrict__ dus, const uint8_t *__restrict__ mask,
@@ -89,21 +75,12 @@ __device__ __forceinline__ uint8_t classify_row(int64_t i, const float *__restri
   return c;
 }
 
-__global__ void k_density_classify(int64_t N, const float *__restrict__ alphas_raw,
-                                   const float *__restrict__ scales_raw, const float *__restrict__ acc,
-                                   const int32_t *__restrict__ cnt, float alpha_raw_min, float scale_raw_max,
-                                   float grad_min, float scale_clone_max, uint8_t *__restrict__ cls) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= N) return;
-  cls[i] = classify_row(i, alphas_raw, scales_raw, acc, cnt, alpha_raw_min, scale_raw_max, grad_min, scale_clone_max);
-}
-
 // ---- the slots (exclusive scan of the three class counters in row order), hand-written:
 //   k_density_classify_count  classify 1024 rows per CTA and leave the CTA's three counts;
 //   k_density_scan_blocks     one CTA turns the per-CTA counts into exclusive offsets + totals;
 //   k_density_slots           every CTA re-reads its 1024 class bytes (4 consecutive rows per
 //                             thread), scans them locally and writes the 12-byte slots.
-// 25 B per Gaussian in total; the three launches replace cub::DeviceScan over a 12-byte struct.
+// 25 B per Gaussian in total; three launches (round 1 used a library scan over the 12-byte struct: 0.034 ms against 0.023).
 constexpr int SC_THREADS = 256, SC_PER = 4, SC_ROWS = SC_THREADS * SC_PER;
 
 __global__ void __launch_bounds__(SC_THREADS) k_density_classify_count(
@@ -209,17 +186,6 @@ __global__ void __launch_bounds__(SC_THREADS) k_density_slots(int64_t N, const u
   for (int j = 0; j < SC_PER; j++) {
     if (row0 + j < N) slots[row0 + j] = run;
     run.k += c[j] != CLS_PRUNE, run.c += c[j] == CLS_CLONE, run.s += c[j] == CLS_SPLIT;
-  }
-}
-
-__global__ void k_density_totals(int64_t N, const uint8_t *__restrict__ cls, const Slot3 *__restrict__ slots,
-                                 int64_t *__restrict__ totals) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) {
-    Slot3 t = slots[N - 1];
-    const Slot3 l = ClsToSlot()(cls[N - 1]);
-    totals[0] = t.k + l.k;
-    totals[1] = t.c + l.c;
-    totals[2] = t.s + l.s;
   }
 }
 
@@ -356,7 +322,7 @@ __device__ __forceinline__ float new_row_value(float val, bool split, int64_t i,
   return nv;
 }
 
-template <int A, int SET>
+template <int A, int SET, bool FIXED>
 __device__ __forceinline__ void rows_job(int row0, int rows_here, const int2 *__restrict__ tab, int K, int C,
                                          const Sets &S, const float *__restrict__ z, int lane) {
   constexpr int w = kWidth[A];
@@ -374,29 +340,91 @@ __device__ __forceinline__ void rows_job(int row0, int rows_here, const int2 *__
     if (SET == 0) nv = new_row_value<A>(val, cl == CLS_SPLIT, (int64_t)row0 + r, info.y - K - C, col, S, z);
     dst[(size_t)info.y * w + col] = nv;
   };
-  constexpr int U = w >= 16 ? 8 : (w >= 3 ? 3 : 1);  // loads in flight per lane (w = 3: 96 elements = 3 rounds)
-  const int nelem = rows_here * w;
+  const int2 pruned = make_int2((int)((unsigned)CLS_PRUNE << 30), 0);
+  // FIXED paths: table entries of rows past the end of the array are CLS_PRUNE, so no row bound
+  // is checked; destination element indices fit 32 bits (2 N * 45 < 2^32 for N < 23 M)
+  constexpr bool plain = SET != 0 || A == 1 || A == 2;  // the new row is a copy (parameters) or zero (moments)
+  auto emit_fixed = [&](int r, int col, int2 info, float val) {
+    if constexpr (plain) {  // two predicated stores, no branches
+      const unsigned cl = (unsigned)info.x >> 30;
+      if (cl != CLS_PRUNE) dst[(unsigned)(info.x & 0x3fffffff) * w + col] = val;
+      if (cl == CLS_CLONE || cl == CLS_SPLIT) dst[(unsigned)info.y * w + col] = SET == 0 ? val : 0.f;
+    } else {
+      emit(r, col, info, val);
+    }
+  };
+  if constexpr (FIXED && w == 45) {
+    // Two rows = 90 elements = three rounds of 32 lanes (94 % of the lanes busy): which of the two
+    // rows and which column a lane handles in each round does not depend on the pair, so the
+    // division by 45 of the generic loop disappears; two pairs (six loads) in flight per lane.
+    const int rsel[3] = {0, lane >= 13, 1};
+    const int col[3] = {lane, lane < 13 ? 32 + lane : lane - 13, 19 + lane};
 #pragma unroll 1
-  for (int e0 = 0; e0 < nelem; e0 += 32 * U) {
-    float v[U];
-    int2 info[U];
-    int r[U];
+    for (int p0 = 0; p0 < 16; p0 += 2) {
+      float v[2][3];
+      int2 info[2][3];
 #pragma unroll
-    for (int u = 0; u < U; u++) {  // all loads are issued before any is consumed
-      const int e = e0 + 32 * u + lane;
-      info[u] = make_int2((int)((unsigned)CLS_PRUNE << 30), 0);
-      r[u] = e / w;
-      if (e < nelem) {
-        info[u] = tab[r[u]];
-        if (((unsigned)info[u].x >> 30) != CLS_PRUNE) v[u] = __ldg(gsrc + e);
-      }
+      for (int q = 0; q < 2; q++)
+#pragma unroll
+        for (int rd = 0; rd < 3; rd++) {
+          info[q][rd] = tab[2 * (p0 + q) + rsel[rd]];
+          if (rd == 2 && lane >= 26) info[q][rd] = pruned;  // 90 elements: the third round has 26
+        }
+#pragma unroll
+      for (int q = 0; q < 2; q++)
+#pragma unroll
+        for (int rd = 0; rd < 3; rd++) {  // all loads are issued before any is consumed
+          v[q][rd] = 0.f;
+          if (((unsigned)info[q][rd].x >> 30) != CLS_PRUNE)
+            v[q][rd] = __ldg(gsrc + (2 * (p0 + q) + rsel[rd]) * w + col[rd]);
+        }
+#pragma unroll
+      for (int q = 0; q < 2; q++)
+#pragma unroll
+        for (int rd = 0; rd < 3; rd++) emit_fixed(2 * (p0 + q) + rsel[rd], col[rd], info[q][rd], v[q][rd]);
+    }
+  } else if constexpr (FIXED) {
+    // w = 1, 3, 4: the whole group is w rounds of 32 lanes, row and column of a lane's element in
+    // round u are the same for every group (hoisted out of the group loop by the compiler)
+    float v[w];
+    int2 info[w];
+#pragma unroll
+    for (int u = 0; u < w; u++) info[u] = tab[(32 * u + lane) / w];
+#pragma unroll
+    for (int u = 0; u < w; u++) {
+      v[u] = 0.f;
+      if (((unsigned)info[u].x >> 30) != CLS_PRUNE) v[u] = __ldg(gsrc + 32 * u + lane);
     }
 #pragma unroll
-    for (int u = 0; u < U; u++) emit(r[u], e0 + 32 * u + lane - r[u] * w, info[u], v[u]);
+    for (int u = 0; u < w; u++) {
+      const int e = 32 * u + lane, r = e / w;
+      emit_fixed(r, e - r * w, info[u], v[u]);
+    }
+  } else {
+    constexpr int U = w >= 16 ? 8 : (w >= 3 ? 3 : 1);  // loads in flight per lane (w = 3: 96 elements = 3 rounds)
+    const int nelem = rows_here * w;
+#pragma unroll 1
+    for (int e0 = 0; e0 < nelem; e0 += 32 * U) {
+      float v[U];
+      int2 info[U];
+      int r[U];
+#pragma unroll
+      for (int u = 0; u < U; u++) {  // all loads are issued before any is consumed
+        const int e = e0 + 32 * u + lane;
+        info[u] = pruned;
+        r[u] = e / w;
+        if (e < nelem) {
+          info[u] = tab[r[u]];
+          if (((unsigned)info[u].x >> 30) != CLS_PRUNE) v[u] = __ldg(gsrc + e);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; u++) emit(r[u], e0 + 32 * u + lane - r[u] * w, info[u], v[u]);
+    }
   }
 }
 
-template <int A, int SET>
+template <int A, int SET, bool FIXED>
 __device__ __noinline__ void rows_loop(int N, const uint8_t *__restrict__ cls, const Slot3 *__restrict__ slots, int K,
                                        int C, const Sets &S, const float *__restrict__ z, int2 *tab) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -412,11 +440,12 @@ __device__ __noinline__ void rows_loop(int N, const uint8_t *__restrict__ cls, c
     // (class | survivor slot, new-row slot); slots < N < 2^30
     tab[lane] = make_int2((int)((unsigned)c << 30) | sl.k, c == CLS_SPLIT ? K + C + sl.s : K + sl.c);
     __syncwarp();
-    rows_job<A, SET>(row0, min(32, N - row0), tab, K, C, S, z, lane);
+    rows_job<A, SET, FIXED>(row0, min(32, N - row0), tab, K, C, S, z, lane);
     __syncwarp();  // the table is rewritten for the next group
   }
 }
 
+template <bool FIXED>
 __global__ void __launch_bounds__(32 * DG_WARPS) k_density_apply_rows(int N, const uint8_t *__restrict__ cls,
                                                                        const Slot3 *__restrict__ slots, int K, int C,
                                                                        const __grid_constant__ Sets S,
@@ -424,7 +453,7 @@ __global__ void __launch_bounds__(32 * DG_WARPS) k_density_apply_rows(int N, con
   __shared__ int2 tabs[DG_WARPS][32];
   int2 *tab = tabs[threadIdx.x >> 5];
 #define GSB_JOB(y, a, s) \
-  case y: rows_loop<a, s>(N, cls, slots, K, C, S, z, tab); break;
+  case y: rows_loop<a, s, FIXED>(N, cls, slots, K, C, S, z, tab); break;
   switch (blockIdx.y) {
     GSB_JOB(0, 2, 0) GSB_JOB(1, 2, 1) GSB_JOB(2, 2, 2) GSB_JOB(3, 0, 0) GSB_JOB(4, 0, 1) GSB_JOB(5, 0, 2)
     GSB_JOB(6, 1, 0) GSB_JOB(7, 1, 1) GSB_JOB(8, 1, 2) GSB_JOB(9, 3, 0) GSB_JOB(10, 3, 1) GSB_JOB(11, 3, 2)
@@ -535,11 +564,8 @@ inline int stream_grid(int64_t total, int block) {
 }  // namespace
 
 size_t density_workspace_bytes(int64_t N) {
-  size_t tmp = 0;
-  thrust::transform_iterator<ClsToSlot, const uint8_t *, Slot3> it(static_cast<const uint8_t *>(nullptr), ClsToSlot());
-  cub::DeviceScan::ExclusiveScan(nullptr, tmp, it, (Slot3 *)nullptr, SlotAdd(), Slot3{0, 0, 0}, (int)(N > 0 ? N : 1));
-  const size_t mine = (size_t)((N + SC_ROWS - 1) / SC_ROWS + 1) * 3 * sizeof(int32_t);
-  return 256 + (tmp > mine ? tmp : mine);  // [three int64 totals, padded to 256 B][per-CTA counts | CUB temp (A/B)]
+  // [three int64 totals, padded to 256 B][three counts per 1024-row CTA]
+  return 256 + (size_t)((N + SC_ROWS - 1) / SC_ROWS + 1) * 3 * sizeof(int32_t);
 }
 
 int launch_density_accumulate(int64_t N, const float *dloss_dus, const uint8_t *mask, float *grad_accum,
@@ -558,46 +584,19 @@ int launch_density_plan(int64_t N, const float *alphas_raw, const float *scales_
                         int64_t *counts_host, cudaStream_t st) {
   counts_host[0] = counts_host[1] = counts_host[2] = 0;
   if (N == 0) return 0;
-  static const int scan_variant = [] {  // 1 = the three hand-written kernels (default), 0 = cub::DeviceScan (A/B)
-    const char *e = getenv("GSB_DENSITY_SCAN_VARIANT");
-    return e != nullptr ? atoi(e) : GSB_DENSITY_DEFAULT_VARIANT;
-  }();
-  if (scan_variant == 1) {
-    int64_t *totals = static_cast<int64_t *>(ws);
-    int32_t *block_counts = reinterpret_cast<int32_t *>(static_cast<char *>(ws) + 256);
-    const int nb = (int)((N + SC_ROWS - 1) / SC_ROWS);
-    {
-      ProfScope ps(K_DENSITY_CLASSIFY, st);
-      k_density_classify_count<<<nb, SC_THREADS, 0, st>>>(N, alphas_raw, scales_raw, grad_accum, cunt, alpha_raw_min,
-                                                         scale_raw_max, grad_min, scale_clone_max, cls, block_counts);
-      GSB_CUDA_TRY(cudaGetLastError());
-    }
-    {
-      ProfScope ps(K_DENSITY_SCAN, st);
-      k_density_scan_blocks<<<1, 1024, 0, st>>>(nb, block_counts, totals);
-      k_density_slots<<<nb, SC_THREADS, 0, st>>>(N, cls, block_counts, reinterpret_cast<Slot3 *>(slots));
-      GSB_CUDA_TRY(cudaGetLastError());
-    }
-    GSB_CUDA_TRY(cudaMemcpyAsync(counts_host, totals, 3 * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-    GSB_CUDA_TRY(cudaStreamSynchronize(st));
-    return 0;
-  }
+  int64_t *totals = static_cast<int64_t *>(ws);
+  int32_t *block_counts = reinterpret_cast<int32_t *>(static_cast<char *>(ws) + 256);
+  const int nb = (int)((N + SC_ROWS - 1) / SC_ROWS);
   {
     ProfScope ps(K_DENSITY_CLASSIFY, st);
-    k_density_classify<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(N, alphas_raw, scales_raw, grad_accum, cunt,
-                                                                     alpha_raw_min, scale_raw_max, grad_min,
-                                                                     scale_clone_max, cls);
+    k_density_classify_count<<<nb, SC_THREADS, 0, st>>>(N, alphas_raw, scales_raw, grad_accum, cunt, alpha_raw_min,
+                                                       scale_raw_max, grad_min, scale_clone_max, cls, block_counts);
     GSB_CUDA_TRY(cudaGetLastError());
   }
-  int64_t *totals = static_cast<int64_t *>(ws);
-  void *scan_tmp = static_cast<char *>(ws) + 256;
-  size_t tmp = ws_bytes - 256;
   {
     ProfScope ps(K_DENSITY_SCAN, st);
-    thrust::transform_iterator<ClsToSlot, const uint8_t *, Slot3> it(static_cast<const uint8_t *>(cls), ClsToSlot());
-    GSB_CUDA_TRY(cub::DeviceScan::ExclusiveScan(scan_tmp, tmp, it, reinterpret_cast<Slot3 *>(slots), SlotAdd(),
-                                               Slot3{0, 0, 0}, (int)N, st));
-    k_density_totals<<<1, 32, 0, st>>>(N, cls, reinterpret_cast<const Slot3 *>(slots), totals);
+    k_density_scan_blocks<<<1, 1024, 0, st>>>(nb, block_counts, totals);
+    k_density_slots<<<nb, SC_THREADS, 0, st>>>(N, cls, block_counts, reinterpret_cast<Slot3 *>(slots));
     GSB_CUDA_TRY(cudaGetLastError());
   }
   GSB_CUDA_TRY(cudaMemcpyAsync(counts_host, totals, 3 * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
@@ -623,14 +622,18 @@ int launch_density_apply(int64_t N, const uint8_t *cls, const int32_t *slots, in
     const char *e = getenv("GSB_DENSITY_VARIANT");
     return e != nullptr ? atoi(e) : GSB_DENSITY_DEFAULT_VARIANT;
   }();
-  if (variant == 1 && N < 23000000) {
+  if (variant >= 1 && N < 23000000) {
     int dev = 0, sms = 148;
     GSB_CUDA_TRY(cudaGetDevice(&dev));
     GSB_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const int64_t blocks = (N + 32 * DG_WARPS - 1) / (32 * DG_WARPS);
     const int grid_x = (int)(blocks < (int64_t)sms * 8 ? blocks : (int64_t)sms * 8);
-    k_density_apply_rows<<<dim3(grid_x, 18), 32 * DG_WARPS, 0, st>>>((int)N, cls, reinterpret_cast<const Slot3 *>(slots), (int)K,
-                                                          (int)C, S, z);
+    if (variant == 2)  // fixed lane -> (row, column) maps: no division per element
+      k_density_apply_rows<true><<<dim3(grid_x, 18), 32 * DG_WARPS, 0, st>>>(
+          (int)N, cls, reinterpret_cast<const Slot3 *>(slots), (int)K, (int)C, S, z);
+    else
+      k_density_apply_rows<false><<<dim3(grid_x, 18), 32 * DG_WARPS, 0, st>>>(
+          (int)N, cls, reinterpret_cast<const Slot3 *>(slots), (int)K, (int)C, S, z);
     GSB_CUDA_TRY(cudaGetLastError());
     return 0;
   }
