@@ -482,8 +482,14 @@ __global__ void __launch_bounds__(RX_THREADS, sizeof(KeyT) == 8 ? 2 : RX_MINBLOC
 
 template <typename KeyT>
 __global__ void __launch_bounds__(256) k_ranges(const uint32_t *__restrict__ P_dev, uint32_t capacity,
+                                                const uint32_t *__restrict__ flags,
                                                 const KeyT *__restrict__ keys, int shift, uint32_t T,
                                                 int2 *__restrict__ ranges) {
+  // After a capacity overflow (k_keys dropped the Gaussians that did not fit) the key / id arrays
+  // have holes with stale contents: every range stays empty (the memset before the sort), so that
+  // the rasterizer enqueued behind this kernel touches no patch and gathers no record through a
+  // stale id.  The frame is discarded and redone by the caller anyway.
+  if (*flags != 0) return;
   const uint32_t P = min(*P_dev, capacity);
   for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < P; p += gridDim.x * blockDim.x) {
     const uint32_t t = (uint32_t)(keys[p] >> shift);
@@ -643,7 +649,7 @@ static int keys_sort_ranges(int N, int64_t P_cap, const float *depths, const uin
     ProfScope ps(K_RANGES, st);
     const size_t want = (size_t)((P_cap + 255) / 256);
     const int grid = (int)(want < (size_t)sms * 8 ? want : (size_t)sms * 8);
-    k_ranges<KeyT><<<grid, 256, 0, st>>>(P_dev, (uint32_t)P_cap, kin, kp.shift, (uint32_t)T,
+    k_ranges<KeyT><<<grid, 256, 0, st>>>(P_dev, (uint32_t)P_cap, total + 2, kin, kp.shift, (uint32_t)T,
                                          reinterpret_cast<int2 *>(ranges));
   }
   GSB_CUDA_TRY(cudaGetLastError());

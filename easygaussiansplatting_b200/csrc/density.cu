@@ -23,7 +23,7 @@
 #include "kernels.h"
 
 #ifndef GSB_DENSITY_DEFAULT_VARIANT
-#define GSB_DENSITY_DEFAULT_VARIANT 1
+#define GSB_DENSITY_DEFAULT_VARIANT 2
 #endif
 
 namespace gsb {
@@ -322,7 +322,7 @@ __device__ __forceinline__ float new_row_value(float val, bool split, int64_t i,
   return nv;
 }
 
-template <int A, int SET, bool FIXED>
+template <int A, int SET, int FIXED>  // FIXED: 0 = generic loop, else pairs of wide rows in flight per lane
 __device__ __forceinline__ void rows_job(int row0, int rows_here, const int2 *__restrict__ tab, int K, int C,
                                          const Sets &S, const float *__restrict__ z, int lane) {
   constexpr int w = kWidth[A];
@@ -353,25 +353,25 @@ __device__ __forceinline__ void rows_job(int row0, int rows_here, const int2 *__
       emit(r, col, info, val);
     }
   };
-  if constexpr (FIXED && w == 45) {
+  if constexpr (FIXED != 0 && w == 45) {
     // Two rows = 90 elements = three rounds of 32 lanes (94 % of the lanes busy): which of the two
     // rows and which column a lane handles in each round does not depend on the pair, so the
-    // division by 45 of the generic loop disappears; two pairs (six loads) in flight per lane.
+    // division by 45 of the generic loop disappears; FIXED pairs (3 FIXED loads) in flight per lane.
     const int rsel[3] = {0, lane >= 13, 1};
     const int col[3] = {lane, lane < 13 ? 32 + lane : lane - 13, 19 + lane};
 #pragma unroll 1
-    for (int p0 = 0; p0 < 16; p0 += 2) {
-      float v[2][3];
-      int2 info[2][3];
+    for (int p0 = 0; p0 < 16; p0 += FIXED) {
+      float v[FIXED][3];
+      int2 info[FIXED][3];
 #pragma unroll
-      for (int q = 0; q < 2; q++)
+      for (int q = 0; q < FIXED; q++)
 #pragma unroll
         for (int rd = 0; rd < 3; rd++) {
           info[q][rd] = tab[2 * (p0 + q) + rsel[rd]];
           if (rd == 2 && lane >= 26) info[q][rd] = pruned;  // 90 elements: the third round has 26
         }
 #pragma unroll
-      for (int q = 0; q < 2; q++)
+      for (int q = 0; q < FIXED; q++)
 #pragma unroll
         for (int rd = 0; rd < 3; rd++) {  // all loads are issued before any is consumed
           v[q][rd] = 0.f;
@@ -379,11 +379,11 @@ __device__ __forceinline__ void rows_job(int row0, int rows_here, const int2 *__
             v[q][rd] = __ldg(gsrc + (2 * (p0 + q) + rsel[rd]) * w + col[rd]);
         }
 #pragma unroll
-      for (int q = 0; q < 2; q++)
+      for (int q = 0; q < FIXED; q++)
 #pragma unroll
         for (int rd = 0; rd < 3; rd++) emit_fixed(2 * (p0 + q) + rsel[rd], col[rd], info[q][rd], v[q][rd]);
     }
-  } else if constexpr (FIXED) {
+  } else if constexpr (FIXED != 0) {
     // w = 1, 3, 4: the whole group is w rounds of 32 lanes, row and column of a lane's element in
     // round u are the same for every group (hoisted out of the group loop by the compiler)
     float v[w];
@@ -424,7 +424,7 @@ __device__ __forceinline__ void rows_job(int row0, int rows_here, const int2 *__
   }
 }
 
-template <int A, int SET, bool FIXED>
+template <int A, int SET, int FIXED>
 __device__ __noinline__ void rows_loop(int N, const uint8_t *__restrict__ cls, const Slot3 *__restrict__ slots, int K,
                                        int C, const Sets &S, const float *__restrict__ z, int2 *tab) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -445,7 +445,7 @@ __device__ __noinline__ void rows_loop(int N, const uint8_t *__restrict__ cls, c
   }
 }
 
-template <bool FIXED>
+template <int FIXED>
 __global__ void __launch_bounds__(32 * DG_WARPS) k_density_apply_rows(int N, const uint8_t *__restrict__ cls,
                                                                        const Slot3 *__restrict__ slots, int K, int C,
                                                                        const __grid_constant__ Sets S,
@@ -628,12 +628,14 @@ int launch_density_apply(int64_t N, const uint8_t *cls, const int32_t *slots, in
     GSB_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const int64_t blocks = (N + 32 * DG_WARPS - 1) / (32 * DG_WARPS);
     const int grid_x = (int)(blocks < (int64_t)sms * 8 ? blocks : (int64_t)sms * 8);
-    if (variant == 2)  // fixed lane -> (row, column) maps: no division per element
-      k_density_apply_rows<true><<<dim3(grid_x, 18), 32 * DG_WARPS, 0, st>>>(
-          (int)N, cls, reinterpret_cast<const Slot3 *>(slots), (int)K, (int)C, S, z);
-    else
-      k_density_apply_rows<false><<<dim3(grid_x, 18), 32 * DG_WARPS, 0, st>>>(
-          (int)N, cls, reinterpret_cast<const Slot3 *>(slots), (int)K, (int)C, S, z);
+    const dim3 grid(grid_x, 18);
+    const Slot3 *sl = reinterpret_cast<const Slot3 *>(slots);
+    if (variant == 3)  // fixed lane -> (row, column) maps, 12 loads in flight per lane for the wide arrays
+      k_density_apply_rows<4><<<grid, 32 * DG_WARPS, 0, st>>>((int)N, cls, sl, (int)K, (int)C, S, z);
+    else if (variant == 2)  // the same with 6 loads in flight
+      k_density_apply_rows<2><<<grid, 32 * DG_WARPS, 0, st>>>((int)N, cls, sl, (int)K, (int)C, S, z);
+    else  // generic loop (one division per element)
+      k_density_apply_rows<0><<<grid, 32 * DG_WARPS, 0, st>>>((int)N, cls, sl, (int)K, (int)C, S, z);
     GSB_CUDA_TRY(cudaGetLastError());
     return 0;
   }

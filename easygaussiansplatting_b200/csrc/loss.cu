@@ -23,9 +23,6 @@
 #ifndef GSB_LOSS_BWD_MINB
 #define GSB_LOSS_BWD_MINB 4
 #endif
-#ifndef GSB_LOSS_DEFAULT_PGU
-#define GSB_LOSS_DEFAULT_PGU 0
-#endif
 
 namespace gsb {
 
@@ -399,11 +396,7 @@ __global__ void __launch_bounds__(32 * SWARPS, GSB_LOSS_FWD_MINB) k_ssim_fwd_row
   }
 }
 
-// PGU: the img / gt values of the output pixel are loaded unconditionally from a clamped (always
-// valid) address.  With a predicated load the compiler loads into a temporary and copies it into
-// the carried register right away -- the copy then waits for the load it was meant to hide
-// (62 % of the kernel's stall samples sat on that MOV, profiles/r2_ncu_loss_density_summary.txt).
-template <bool VEC, bool PGU>
+template <bool VEC>
 __global__ void __launch_bounds__(32 * SWARPS, GSB_LOSS_BWD_MINB) k_ssim_bwd_rows(int W, int H, int SH, const float *__restrict__ img,
                                                                   const float *__restrict__ gt, Win11 win,
                                                                   const float *__restrict__ maps,
@@ -446,12 +439,7 @@ __global__ void __launch_bounds__(32 * SWARPS, GSB_LOSS_BWD_MINB) k_ssim_bwd_row
         const bool emit = t >= 2 * LR && xin;
         const int o = (yy - LR) * W + x;
         const float p = pq[i & 1], g = gq[i & 1];
-        if constexpr (PGU) {  // the pixel iteration t + 2 emits (unused, but in range, when it emits nothing)
-          const int o2 = min(max(yy - LR + 2, 0), H - 1) * W + min(x, W - 1);
-          pq[i & 1] = __ldg(a + o2), gq[i & 1] = __ldg(b + o2);
-        } else {
-          if (t + 2 >= 2 * LR && t + 2 < n && xin) pq[i & 1] = __ldg(a + o + 2 * W), gq[i & 1] = __ldg(b + o + 2 * W);
-        }
+        if (t + 2 >= 2 * LR && t + 2 < n && xin) pq[i & 1] = __ldg(a + o + 2 * W), gq[i & 1] = __ldg(b + o + 2 * W);
         const float *q0 = &line[wid][0][i & 1][lane + SPAD - LR], *q1 = &line[wid][1][i & 1][lane + SPAD - LR],
                     *q2 = &line[wid][2][i & 1][lane + SPAD - LR];
         float2 h01 = make_float2(0.f, 0.f);
@@ -536,18 +524,10 @@ int launch_gau_loss(int H, int W, const float *img, const float *gt, float lambd
     GSB_CUDA_TRY(cudaGetLastError());
     {
       ProfScope ps(K_LOSS_BWD, st);
-      static const int pgu = [] {  // 1 = unconditional pixel loads in the backward kernel (A/B)
-        const char *e = getenv("GSB_LOSS_PGU");
-        return e != nullptr ? atoi(e) : GSB_LOSS_DEFAULT_PGU;
-      }();
-      if (vec && pgu)
-        k_ssim_bwd_rows<true, true><<<grid, 32 * SWARPS, 0, st>>>(W, H, SH, img, gt, win, maps, acc, lambda, loss_out, grad);
-      else if (vec)
-        k_ssim_bwd_rows<true, false><<<grid, 32 * SWARPS, 0, st>>>(W, H, SH, img, gt, win, maps, acc, lambda, loss_out, grad);
-      else if (pgu)
-        k_ssim_bwd_rows<false, true><<<grid, 32 * SWARPS, 0, st>>>(W, H, SH, img, gt, win, maps, acc, lambda, loss_out, grad);
+      if (vec)
+        k_ssim_bwd_rows<true><<<grid, 32 * SWARPS, 0, st>>>(W, H, SH, img, gt, win, maps, acc, lambda, loss_out, grad);
       else
-        k_ssim_bwd_rows<false, false><<<grid, 32 * SWARPS, 0, st>>>(W, H, SH, img, gt, win, maps, acc, lambda, loss_out, grad);
+        k_ssim_bwd_rows<false><<<grid, 32 * SWARPS, 0, st>>>(W, H, SH, img, gt, win, maps, acc, lambda, loss_out, grad);
     }
     GSB_CUDA_TRY(cudaGetLastError());
     return 0;

@@ -263,10 +263,24 @@ def test_capacity_path_equals_exact_path(N, W, H):
         assert torch.equal(a, b) and torch.equal(a, c)
     assert torch.equal(dep0, dep1) and torch.equal(ar0, ar1)
     P = exact[4].numel()
+
+    def poison():
+        """fill the caching allocator's pool with ids far outside [0, N): after an overflow the key / id
+        arrays have holes the kernels never wrote, and nothing may be gathered through them"""
+        torch.cuda.synchronize()
+        torch.cuda.empty_cache()
+        x = torch.full((64 << 20,), 0x7f7f7f7f, dtype=torch.int32, device=DEV)
+        torch.cuda.synchronize()
+        del x
+
+    poison()
     ops._CAPACITY[key] = (max(1, P // 3), ops._CAPACITY[key][1])  # too few patches
     small, _, _ = run(True)
+    torch.cuda.synchronize()
+    poison()
     ops._CAPACITY[key] = (2 * P + 10, 3)                          # depth keys wider than planned
     narrow, _, _ = run(True)
+    torch.cuda.synchronize()
     for a, b, c in zip(exact, small, narrow):
         assert torch.equal(a, b) and torch.equal(a, c)
     assert ops._CAPACITY[key][0] >= P  # relearnt
@@ -320,6 +334,13 @@ def test_graphed_step_matches_eager_and_detects_overflow():
     us0 = torch.zeros((N, 2), device=DEV, requires_grad=True)
     cam = Camera(W, H, sc["fx"], sc["fy"], sc["cx"], sc["cy"], t(sc["Rcw"]), t(sc["tcw"]), t(sc["twc"]))
     dl = t(upstream_gradient(W, H, 1) * (3.0 * W * H))
+    # the graph's static buffers come out of a pool full of out-of-range ids (see the overflow below)
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+    junk = torch.full((64 << 20,), 0x7f7f7f7f, dtype=torch.int32, device=DEV)
+    torch.cuda.synchronize()
+    del junk
+    torch.cuda.empty_cache()  # (the capture allocates from its own pool: hand the dirty pages back to the driver)
     step = GraphedFusedStep(P["pws"], P["shs"], al, P["scales"], P["rots"], cam)
 
     def eager():
@@ -346,6 +367,7 @@ def test_graphed_step_matches_eager_and_detects_overflow():
     with torch.no_grad():
         P["scales"].mul_(4.0)
     step.forward()
+    torch.cuda.synchronize()  # the overflowing replay itself must be memory-safe
     with pytest.raises(CapacityError):
         step.backward()
     step.recapture()
