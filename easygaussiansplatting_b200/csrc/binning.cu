@@ -303,6 +303,7 @@ __global__ void __launch_bounds__(1024) k_colscan(const uint32_t *__restrict__ P
   __shared__ uint32_t s_part[WARPS][32];
   __shared__ uint32_t s_scan[WARPS];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (P_dev[2] != 0) return;  // [P, max key, flags]: capacity overflow, the frame is abandoned (see k_ranges)
   const uint32_t P = min(*P_dev, capacity);
   const int T = (int)((P + RX_TILE - 1) / RX_TILE);
   {  // exclusive scan of the global digit histogram (BINS <= 1024 = one value per thread)
@@ -362,6 +363,9 @@ __global__ void __launch_bounds__(RX_THREADS, sizeof(KeyT) == 8 ? 2 : RX_MINBLOC
   KeyT *const s_keys = reinterpret_cast<KeyT *>(s_dyn);
   int32_t *const s_vals = reinterpret_cast<int32_t *>(s_dyn + RX_TILE * sizeof(KeyT));
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // Capacity overflow: k_keys left holes with stale keys that no histogram counted, so scatter
+  // positions could run past the buffers.  Nothing is sorted; k_ranges leaves every range empty.
+  if (P_dev[2] != 0) return;
   const uint32_t P = min(*P_dev, capacity);
   const int ntiles = (int)((P + RX_TILE - 1) / RX_TILE);
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -486,9 +490,9 @@ __global__ void __launch_bounds__(256) k_ranges(const uint32_t *__restrict__ P_d
                                                 const KeyT *__restrict__ keys, int shift, uint32_t T,
                                                 int2 *__restrict__ ranges) {
   // After a capacity overflow (k_keys dropped the Gaussians that did not fit) the key / id arrays
-  // have holes with stale contents: every range stays empty (the memset before the sort), so that
-  // the rasterizer enqueued behind this kernel touches no patch and gathers no record through a
-  // stale id.  The frame is discarded and redone by the caller anyway.
+  // have holes with stale contents and were not sorted: every range stays empty (the memset before
+  // the sort), so that the rasterizer enqueued behind this kernel touches no patch and gathers no
+  // record through a stale id.  The frame is discarded and redone by the caller anyway.
   if (*flags != 0) return;
   const uint32_t P = min(*P_dev, capacity);
   for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < P; p += gridDim.x * blockDim.x) {
