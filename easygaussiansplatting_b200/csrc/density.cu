@@ -23,7 +23,7 @@
 #include "kernels.h"
 
 #ifndef GSB_DENSITY_DEFAULT_VARIANT
-#define GSB_DENSITY_DEFAULT_VARIANT 2
+#define GSB_DENSITY_DEFAULT_VARIANT 3
 #endif
 
 namespace gsb {
@@ -618,7 +618,7 @@ int launch_density_apply(int64_t N, const uint8_t *cls, const int32_t *slots, in
     S.dv[a] = dst_v ? dst_v[a] : nullptr;
   }
   ProfScope ps(K_DENSITY_APPLY, st);
-  static const int variant = [] {  // 1 = row groups (default), 0 = one element per thread (A/B)
+  static const int variant = [] {  // 3 (default) / 2 / 1 = row groups (see the launch below), 0 = one element per thread
     const char *e = getenv("GSB_DENSITY_VARIANT");
     return e != nullptr ? atoi(e) : GSB_DENSITY_DEFAULT_VARIANT;
   }();
