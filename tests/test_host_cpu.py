@@ -35,6 +35,29 @@ def test_library_exports_every_declared_symbol():
     assert "draw" in names and "draw_backward" in names
 
 
+def test_no_library_kernels_and_host_only_entry_points():
+    """the binary holds no CUB / thrust kernel (round 1 sorted and scanned with them), and the
+    host-only workspace queries answer without a GPU"""
+    from easygaussiansplatting_b200 import _lib, build
+    build.build()
+    lib = _lib.load()
+    r = subprocess.run(["cuobjdump", "-elf", "-symbols", _lib.LIB_PATH], capture_output=True, text=True)
+    kernels = [ln for ln in r.stdout.splitlines() if "STT_FUNC" in ln]
+    assert len(kernels) > 30
+    assert not [ln for ln in kernels if "cub" in ln or "thrust" in ln], "a library kernel is linked in"
+    for name in ("k_rects_scan", "k_radix_pass", "k_colscan", "k_density_slots", "k_density_apply_rows",
+                 "k_ssim_fwd_rows", "k_ssim_bwd_rows", "k_draw3", "k_draw_bwd4"):
+        assert any(name in ln for ln in kernels), name
+    prev = 0
+    for n in (0, 1, 1000, 1 << 20, 5 << 20):
+        b = lib.gsb_density_workspace_bytes(n)
+        assert b >= 256 + 12 * (n // 1024) and b >= prev
+        prev = b
+    assert lib.gsb_gau_loss_workspace_bytes(1080, 1920) >= 9 * 4 * 1080 * 1920
+    assert lib.gsb_splat_bin_workspace_bytes(1000) < lib.gsb_splat_bin_workspace_bytes(1 << 20)
+    assert lib.gsb_splat_workspace_bytes(1000, 64, 64, 10) <= lib.gsb_splat_workspace_bytes(1000, 64, 64, 100000)
+
+
 def test_library_is_sm100a_with_async_record_gather():
     """built for sm_100a; the rasterizers stage records with 16-byte async copies tracked by an
     mbarrier (SASS LDGSTS + LDGSTSBAR arrive-on + SYNCS try-wait) and use packed fp32 math"""
